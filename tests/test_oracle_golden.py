@@ -1,0 +1,202 @@
+"""CPU: pin the oracle restatement against fixtures produced by the REAL
+reference code (oracle/make_golden.py).  Bit-exact for copy/index ops; tight
+fp32 tolerance where torch's summation order inside one op may vary."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import stereo_oracle as so
+
+T = torch.from_numpy
+
+
+def test_concat_volume_bit_exact(golden):
+    g = golden("psmnet_inline")
+    C = g["feat_L"].shape[1]
+    vol = so.concat_volume(T(g["feat_L"]), T(g["feat_R"]), int(g["num_disp"]))
+    # fixture channel order: [left ch..., right ch...] == restatement's [0,C) | [C,2C)
+    assert vol.shape == g["vol"].shape and C * 2 == vol.shape[1]
+    assert np.array_equal(vol.numpy(), g["vol"])
+
+
+def test_soft_argmin_network_logits(golden):
+    g = golden("psmnet_inline")
+    pred = so.soft_argmin(T(g["logits"]))
+    assert np.abs(pred.numpy() - g["pred"]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("tag", ["s1", "s10", "d96"])
+def test_soft_argmin_synth(golden, tag):
+    g = golden("soft_argmin_synth")
+    cost = T(g[f"{tag}_cost"]).requires_grad_(True)
+    pred = so.soft_argmin(cost)
+    pred.backward(T(g[f"{tag}_g"]))
+    assert np.abs(pred.detach().numpy() - g[f"{tag}_pred"]).max() <= 1e-4
+    np.testing.assert_allclose(cost.grad.numpy(), g[f"{tag}_gcost"], rtol=1e-5, atol=1e-6)
+
+
+def test_apply_disparity(golden):
+    g = golden("reprojection")
+    d = T(g["disp"]).requires_grad_(True)
+    img = T(g["R3"]).requires_grad_(True)
+    w = so.apply_disparity(img, -d)
+    w.backward(T(g["warp3_gout"]))
+    assert np.array_equal(w.detach().numpy(), g["warp3"])
+    np.testing.assert_allclose(d.grad.numpy(), g["warp3_gdisp"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(img.grad.numpy(), g["warp3_gimg"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(so.apply_disparity(T(g["L1"]), T(g["disp_r"])).numpy(), g["warp1_pos"])
+
+
+@pytest.mark.parametrize("tag,img,masked", [("old1m", "1", True), ("old3m", "3", True), ("old1", "1", False)])
+def test_reproj_old(golden, tag, img, masked):
+    g = golden("reprojection")
+    d = T(g["disp"]).requires_grad_(True)
+    loss, warped, mi = so.reproj_error_old(T(g["L" + img]), T(g["R" + img]), d, T(g["mask"]) if masked else None)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g[f"{tag}_loss"], rtol=1e-6)
+    assert np.array_equal(warped.detach().numpy(), g[f"{tag}_warped"])
+    assert np.array_equal(mi.numpy(), g[f"{tag}_mask"]) and mi.dtype == torch.int32
+    np.testing.assert_allclose(d.grad.numpy(), g[f"{tag}_gdisp"], rtol=1e-5, atol=1e-9)
+
+
+def test_reproj_bidir(golden):
+    g = golden("reprojection")
+    dl = T(g["disp"]).requires_grad_(True)
+    dr = T(g["disp_r"]).requires_grad_(True)
+    ll, lr, wl, wr, ml, mr = so.reproj_error_bidir(T(g["L3"]), T(g["R3"]), dl, dr, T(g["mask"]), T(g["mask_r"]))
+    (ll + 2 * lr).backward()
+    np.testing.assert_allclose(ll.item(), g["bi_loss_l"], rtol=1e-6)
+    np.testing.assert_allclose(lr.item(), g["bi_loss_r"], rtol=1e-6)
+    assert np.array_equal(wl.detach().numpy(), g["bi_warp_l"]) and np.array_equal(wr.detach().numpy(), g["bi_warp_r"])
+    assert np.array_equal(ml.numpy(), g["bi_mask_l"]) and np.array_equal(mr.numpy(), g["bi_mask_r"])
+    np.testing.assert_allclose(dl.grad.numpy(), g["bi_gdisp_l"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(dr.grad.numpy(), g["bi_gdisp_r"], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("tag,img,masked,ps", [("p5m", "1", True, 5), ("p11m", "1", True, 11), ("p11", "1", False, 11),
+                                                ("p3c3m", "3", True, 3), ("p1m", "1", True, 1)])
+def test_reproj_patch(golden, tag, img, masked, ps):
+    g = golden("reprojection")
+    d = T(g["disp"]).requires_grad_(True)
+    loss, vis, mi = so.reproj_error_patch(T(g["L" + img]), T(g["R" + img]), d, T(g["mask"]) if masked else None, ps=ps)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g[f"{tag}_loss"], rtol=1e-6)
+    np.testing.assert_allclose(vis.detach().numpy(), g[f"{tag}_vis"], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(mi.numpy(), g[f"{tag}_mask"])
+    np.testing.assert_allclose(d.grad.numpy(), g[f"{tag}_gdisp"], rtol=1e-5, atol=1e-9)
+
+
+def test_reproj_patch_empty_mask_is_nan(golden):
+    g = golden("reprojection")
+    assert np.isnan(g["p5empty_loss"])
+    loss, _, _ = so.reproj_error_patch(T(g["L1"]), T(g["R1"]), T(g["disp"]), torch.zeros(2, 1, 24, 40, dtype=torch.bool), ps=5)
+    assert torch.isnan(loss)
+
+
+def test_patch_closed_form_matches_reference(golden):
+    """The float64 closed form (two composed border rules) that the CUDA kernel
+    implements reproduces the reference's loss and disparity gradient."""
+    g = golden("reprojection")
+    # d(loss)/d(disp) jumps where the sample position crosses an integer; the
+    # fp32 reference and the fp64 closed form may floor differently there.
+    xs, _ = so.sample_coords(-T(g["disp"]), 24, 40, torch.float64)
+    smooth = (np.abs(xs.numpy() - np.round(xs.numpy())) > 1e-3)[:, None]
+    for tag, ps, masked in (("p5m", 5, True), ("p11", 11, False)):
+        loss, grad = so.patch_loss_closed_form(g["L1"], g["R1"], g["disp"], g["mask"] if masked else None, ps)
+        np.testing.assert_allclose(loss, g[f"{tag}_loss"], rtol=2e-6)
+        np.testing.assert_allclose(grad[smooth], g[f"{tag}_gdisp"][smooth], rtol=2e-4, atol=2e-8)
+        assert smooth.mean() > 0.99
+
+
+def test_reproj_diff_ratio(golden):
+    g = golden("reprojection")
+    d = T(g["disp"]).requires_grad_(True)
+    tot, stages, ld = so.reproj_error_diff_ratio(T(g["L3"]), T(g["R3"]), d, T(g["mask"]))
+    tot.backward()
+    np.testing.assert_allclose(tot.item(), g["ms_loss"], rtol=1e-6)
+    np.testing.assert_allclose(d.grad.numpy(), g["ms_gdisp"], rtol=1e-5, atol=1e-9)
+    for k in range(3):
+        np.testing.assert_allclose(ld[f"stage{k}"], g[f"ms_stage{k}_loss"], rtol=1e-6)
+        assert np.array_equal(stages[f"stage{k}"]["warped"].detach().numpy(), g[f"ms_stage{k}_warped"])
+        assert np.array_equal(stages[f"stage{k}"]["mask"].numpy(), g[f"ms_stage{k}_mask"])
+
+
+def test_lcn(golden):
+    g = golden("reprojection")
+    n9, s9 = so.local_contrast_norm(T(g["lcn_img"]), 9)
+    n5, s5 = so.local_contrast_norm(T(g["lcn_img"]), 5, eps=1e-3)
+    np.testing.assert_allclose(n9.numpy(), g["lcn9_norm"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(s9.numpy(), g["lcn9_std"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(n5.numpy(), g["lcn5_norm"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(s5.numpy(), g["lcn5_std"], rtol=1e-6, atol=1e-7)
+
+
+def test_scatter_warp_bit_exact(golden):
+    g = golden("scatter_warp")
+    img = T(g["img"])
+    assert np.array_equal(so.scatter_warp(img, T(g["disp_pos"])).numpy(), g["out_pos"])
+    assert np.array_equal(so.scatter_warp(img, T(g["disp_neg"])).numpy(), g["out_neg"])
+    assert np.array_equal(so.scatter_warp(T(g["self_img"]), T(g["self_disp"])).numpy(), g["self_out"])
+
+
+def test_scatter_warp_largest_abs_disp_wins(golden):
+    """sequential last-writer-wins == 'largest |disp| landing on
+    idx wins' -- the rule the parallel CUDA kernel implements."""
+    g = golden("scatter_warp")
+    for dk, ok in (("disp_pos", "out_pos"), ("disp_neg", "out_neg")):
+        img, d = g["img"], g[dk]
+        N, C, H, W = img.shape
+        out = np.zeros_like(img)
+        best = np.full((N, C, H, W), -1, np.int64)
+        for j in range(W):
+            idx = j + d[:, 0, :, j]
+            for n in range(N):
+                for y in range(H):
+                    t = idx[n, y]
+                    if 0 <= t < W and abs(d[n, 0, y, j]) > best[n, 0, y, t]:
+                        best[n, :, y, t] = abs(d[n, 0, y, j])
+                        out[n, :, y, t] = img[n, :, y, j]
+        assert np.array_equal(out, g[ok])
+
+
+def test_temporal_ir(golden):
+    g = golden("temporal_ir")
+    for side in ("L", "R"):
+        pat = so.temporal_ir_pattern(g[f"frames_{side}"])
+        assert np.array_equal(pat, g[f"pattern_{side}"])
+        pat_np = so.temporal_ir_pattern(g[f"frames_{side}"], use_cv2=False)
+        assert (pat_np != g[f"pattern_{side}"]).mean() < 1e-3
+    assert 0.01 < g["pattern_L"].mean() < 0.5  # the synthetic dots are detected
+
+
+def test_c_restatement(tmp_path, golden):
+    """oracle/c/stereo_oracle.c agrees with the fixtures too."""
+    src = os.path.join(os.path.dirname(so.__file__), "c", "stereo_oracle.c")
+    lib_path = str(tmp_path / "libstereo_oracle.so")
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", src, "-o", lib_path, "-lm"])
+    lib = ctypes.CDLL(lib_path)
+    vp = ctypes.c_void_p
+    g = golden("scatter_warp")
+    img = np.ascontiguousarray(g["img"])
+    N, C, H, W = img.shape
+    for dk, ok, pos in (("disp_pos", "out_pos", 1), ("disp_neg", "out_neg", 0)):
+        out = np.zeros_like(img)
+        d = np.ascontiguousarray(g[dk])
+        lib.azo_scatter_warp(vp(out.ctypes.data), vp(img.ctypes.data), vp(d.ctypes.data), N, C, H, W, pos)
+        assert np.array_equal(out, g[ok])
+    g = golden("psmnet_inline")
+    L, R = np.ascontiguousarray(g["feat_L"]), np.ascontiguousarray(g["feat_R"])
+    B, C, H, W = L.shape
+    Dq = int(g["num_disp"])
+    vol = np.empty((B, 2 * C, Dq, H, W), np.float32)
+    lib.azo_concat_volume(vp(vol.ctypes.data), vp(L.ctypes.data), vp(R.ctypes.data), B, C, Dq, H, W)
+    assert np.array_equal(vol, g["vol"])
+    logits = np.ascontiguousarray(g["logits"])
+    B, D, H, W = logits.shape
+    out = np.empty((B, 1, H, W), np.float64)
+    lib.azo_soft_argmin_f64(vp(out.ctypes.data), vp(logits.ctypes.data), B, D, H, W)
+    assert np.abs(out - g["pred"]).max() <= 1e-4
