@@ -1,0 +1,106 @@
+// Shared device/host helpers for libaz_stereo (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/az_stereo.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libaz_stereo is written for sm_100a (B200) only"
+#endif
+
+#define AZ_LAUNCH_CHECK() \
+    do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
+namespace az {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- streaming (evict-first) 128-bit / 32-bit global accesses ---------------------------
+// The volumes (0.4-3.2 GB) are far larger than the 126 MB L2 and are consumed by a later
+// kernel (cuDNN), so they are written/read with the .cs policy to keep L2 for the small inputs.
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) -----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared::cta bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- block reductions ---------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Sum over the CTA; result valid in thread 0.  `scratch` holds >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (wid == 0) {
+        r = lane < nw ? scratch[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// ---- sample position of apply_disparity, in the reference's fp32 op order -----------------
+// utils/reprojection.py:15-32 + grid_sample's unnormalise (align_corners=False):
+//   f = lin[j] + disp/W;  g = 2*f - 1;  xs = ((g + 1) * W - 1) / 2
+// torch's CPU grid_sampler fuses the (g+1)*W-1 step into one FMA (verified bit-for-bit against
+// F.grid_sample in the authoring container), so the same contraction is spelled out here and
+// everything else is kept un-fused with the _rn intrinsics.
+__device__ __forceinline__ float sample_pos(float lin, float shift, float size) {
+    const float f = __fadd_rn(lin, shift);
+    const float g = __fsub_rn(__fmul_rn(2.0f, f), 1.0f);
+    return __fmul_rn(__fmaf_rn(__fadd_rn(g, 1.0f), size, -1.0f), 0.5f);
+}
+
+}  // namespace az

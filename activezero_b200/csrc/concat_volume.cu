@@ -1,0 +1,332 @@
+// Concat cost volume, forward and backward.
+// Reference: /root/reference/nets/psmnet/psmnet.py:151-165 (= psmnet_3.py:149-163).
+//
+// Forward is a pure store stream (2C*Dq*H*W floats out for 2*C*H*W floats in): each CTA
+// owns a contiguous run of one (b, channel) feature plane, stages it once (left half: in
+// registers; right half: in shared memory as four copies pre-shifted by 0..3 columns behind a
+// zero prefix, so that every disparity shift is an ALIGNED 128-bit shared load), and then
+// sweeps the Dq disparity planes with coalesced, streaming 128-bit stores.  Each right-feature
+// row is read from HBM exactly once per sweep.
+//
+// Backward is a pure load stream.  The gradient slab of one (b, channel, row-tile) -- Dq
+// contiguous runs of rows -- is pulled into shared memory with 1-D bulk async copies (TMA
+// engine, mbarrier completion), all issued up front, and reduced along the disparity axis
+// (left half: straight down; right half: along the x+i diagonal) by one thread per output
+// column, in a fixed order: gather-style and atomic-free.
+#include "common.cuh"
+
+namespace az {
+
+constexpr int kFwdThreads = 256;
+constexpr int kFwdPPT = 2;  // float4 positions per thread
+
+// ------------------------------------------------------------------------------------------
+// forward, vectorised (W % 4 == 0, 16-byte aligned bases)
+// grid = (ceil(H*W/4 / (256*PPT)), 2C, B)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFwdThreads) concat_fwd_vec4_kernel(const float* __restrict__ L,
+                                                                     const float* __restrict__ R,
+                                                                     float* __restrict__ vol, int C, int H,
+                                                                     int W, int Dq, int pad, int rows_cap) {
+    extern __shared__ __align__(16) float smem[];
+    const int W4 = W >> 2;
+    const int P = kFwdThreads * kFwdPPT;
+    const int oc = blockIdx.y, b = blockIdx.z;
+    const bool right = oc >= C;
+    const int c = right ? oc - C : oc;
+    const int p0 = blockIdx.x * P;
+    const int pend = min(p0 + P, H * W4);
+    const size_t HW = (size_t)H * W;
+    const float* src = (right ? R : L) + ((size_t)b * C + c) * HW;
+    float* out = vol + ((size_t)b * 2 * C + oc) * Dq * HW;
+
+    if (!right) {
+        // left half: value is disparity-independent, only the x >= i mask changes.
+        float4 v[kFwdPPT];
+        int x[kFwdPPT];
+        size_t off[kFwdPPT];
+        bool on[kFwdPPT];
+#pragma unroll
+        for (int k = 0; k < kFwdPPT; ++k) {
+            const int p = p0 + threadIdx.x + k * kFwdThreads;
+            on[k] = p < pend;
+            const int pp = on[k] ? p : p0;
+            off[k] = (size_t)pp * 4;
+            x[k] = (pp % W4) * 4;
+            v[k] = __ldg(reinterpret_cast<const float4*>(src + off[k]));
+        }
+        for (int i = 0; i < Dq; ++i) {
+#pragma unroll
+            for (int k = 0; k < kFwdPPT; ++k) {
+                float4 o = v[k];
+                if (x[k] + 3 < i) { o = make_float4(0.f, 0.f, 0.f, 0.f); }
+                else if (x[k] < i) {
+                    if (x[k] + 0 < i) o.x = 0.f;
+                    if (x[k] + 1 < i) o.y = 0.f;
+                    if (x[k] + 2 < i) o.z = 0.f;
+                }
+                if (on[k]) st_stream(reinterpret_cast<float4*>(out + (size_t)i * HW + off[k]), o);
+            }
+        }
+        return;
+    }
+
+    // right half: rows y_first..y_last of the plane, four pre-shifted copies each.
+    const int y_first = p0 / W4;
+    const int y_last = (pend - 1) / W4;
+    const int nrows = y_last - y_first + 1;
+    const int S = pad + W;                        // row stride (floats), multiple of 4
+    const int copy_stride = rows_cap * S;         // floats per shifted copy
+    // zero everything (prefixes + tails), then scatter the four shifted copies
+    for (int t = threadIdx.x; t < copy_stride; t += kFwdThreads)
+        reinterpret_cast<float4*>(smem)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int t = threadIdx.x; t < nrows * W; t += kFwdThreads) {
+        const int y = t / W, xx = t - y * W;
+        const float val = __ldg(src + (size_t)(y_first + y) * W + xx);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (xx + r < W) smem[r * copy_stride + y * S + pad + xx + r] = val;
+    }
+    __syncthreads();
+
+    const float* sp[kFwdPPT];
+    size_t off[kFwdPPT];
+    bool on[kFwdPPT];
+#pragma unroll
+    for (int k = 0; k < kFwdPPT; ++k) {
+        const int p = p0 + threadIdx.x + k * kFwdThreads;
+        on[k] = p < pend;
+        const int pp = on[k] ? p : p0;
+        const int y = pp / W4, x = (pp - y * W4) * 4;
+        off[k] = (size_t)pp * 4;
+        sp[k] = smem + (y - y_first) * S + pad + x;
+    }
+    for (int i = 0; i < Dq; ++i) {
+        const int r = i & 3, k4 = i & ~3;
+#pragma unroll
+        for (int k = 0; k < kFwdPPT; ++k) {
+            const float4 o = *reinterpret_cast<const float4*>(sp[k] + r * copy_stride - k4);
+            if (on[k]) st_stream(reinterpret_cast<float4*>(out + (size_t)i * HW + off[k]), o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward, scalar fallback (any W, any alignment): one thread per output element of a
+// (b, oc, i) plane.  grid = (ceil(H*W/256), Dq, B*2C)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) concat_fwd_scalar_kernel(const float* __restrict__ L,
+                                                                const float* __restrict__ R,
+                                                                float* __restrict__ vol, int C, int H, int W,
+                                                                int Dq) {
+    const int hw = blockIdx.x * 256 + threadIdx.x;
+    if (hw >= H * W) return;
+    const int i = blockIdx.y;
+    const int boc = blockIdx.z, b = boc / (2 * C), oc = boc - b * 2 * C;
+    const int x = hw % W;
+    float v = 0.f;
+    if (x >= i) {
+        if (oc < C) v = __ldg(L + ((size_t)b * C + oc) * H * W + hw);
+        else        v = __ldg(R + ((size_t)b * C + (oc - C)) * H * W + hw - i);
+    }
+    st_stream(vol + (((size_t)boc * Dq + i) * H) * W + hw, v);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, bulk-async-copy path (W % 4 == 0, aligned): grid = (ceil(H/ny), 2C, B)
+// smem: [chunk][ny*W] floats of gradient slab + mbarriers.
+// ------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = 256;
+constexpr int kBwdGroup = 8;  // disparity planes per mbarrier
+
+__global__ void __launch_bounds__(kBwdThreads) concat_bwd_bulk_kernel(const float* __restrict__ gvol,
+                                                                     float* __restrict__ gL,
+                                                                     float* __restrict__ gR, int C, int H,
+                                                                     int W, int Dq, int ny, int chunk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int oc = blockIdx.y, b = blockIdx.z;
+    const bool right = oc >= C;
+    float* gout = right ? gR : gL;
+    if (gout == nullptr) return;
+    const int c = right ? oc - C : oc;
+    const int y0 = blockIdx.x * ny;
+    const int rows = min(ny, H - y0);
+    const int n = rows * W;                     // floats per disparity plane of this tile
+    const int slab = ny * W;                    // smem stride per plane
+    const int ngroups_cap = (chunk + kBwdGroup - 1) / kBwdGroup;
+    float* s = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)chunk * slab * sizeof(float));
+    const size_t HW = (size_t)H * W;
+    const float* gsrc = gvol + ((size_t)b * 2 * C + oc) * Dq * HW + (size_t)y0 * W;
+
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < ngroups_cap; ++g) mbar_init(&bars[g], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    constexpr int kOut = 4;  // outputs per thread (n <= kOut * kBwdThreads is guaranteed by the host)
+    float acc[kOut];
+    int ox[kOut];
+#pragma unroll
+    for (int k = 0; k < kOut; ++k) {
+        acc[k] = 0.f;
+        const int t = threadIdx.x + k * kBwdThreads;
+        ox[k] = t < n ? t % W : -1;
+    }
+
+    uint32_t parity = 0;
+    for (int i0 = 0; i0 < Dq; i0 += chunk) {
+        const int cnt = min(chunk, Dq - i0);
+        const int ngroups = (cnt + kBwdGroup - 1) / kBwdGroup;
+        if (threadIdx.x == 0) {
+            // generic-proxy reads of the previous chunk are ordered before these async writes
+            // by the __syncthreads at the end of the loop body + this proxy fence.
+            fence_proxy_async();
+            for (int g = 0; g < ngroups; ++g) {
+                const int gi0 = g * kBwdGroup, gcnt = min(kBwdGroup, cnt - gi0);
+                mbar_arrive_expect_tx(&bars[g], (uint32_t)(gcnt * n * sizeof(float)));
+                for (int i = gi0; i < gi0 + gcnt; ++i)
+                    bulk_g2s(s + (size_t)i * slab, gsrc + (size_t)(i0 + i) * HW, (uint32_t)(n * sizeof(float)),
+                             &bars[g]);
+            }
+        }
+        for (int g = 0; g < ngroups; ++g) {
+            mbar_wait(&bars[g], parity);
+            const int gi0 = g * kBwdGroup, gcnt = min(kBwdGroup, cnt - gi0);
+#pragma unroll
+            for (int k = 0; k < kOut; ++k) {
+                if (ox[k] < 0) continue;
+                const int t = threadIdx.x + k * kBwdThreads;
+                const float* sp = s + (size_t)gi0 * slab + t;
+                if (right) {
+                    // gR[x] += g[i][x+i]  while x+i < W
+                    for (int i = 0; i < gcnt; ++i) {
+                        const int ii = i0 + gi0 + i;
+                        if (ox[k] + ii < W) acc[k] += sp[(size_t)i * slab + ii];
+                    }
+                } else {
+                    // gL[x] += g[i][x]  while i <= x
+                    for (int i = 0; i < gcnt; ++i) {
+                        const int ii = i0 + gi0 + i;
+                        if (ii <= ox[k]) acc[k] += sp[(size_t)i * slab];
+                    }
+                }
+            }
+        }
+        parity ^= 1;
+        __syncthreads();
+    }
+    float* o = gout + ((size_t)b * C + c) * HW + (size_t)y0 * W;
+#pragma unroll
+    for (int k = 0; k < kOut; ++k)
+        if (ox[k] >= 0) o[threadIdx.x + k * kBwdThreads] = acc[k];
+}
+
+// backward, scalar fallback: one thread per output element.  grid = (ceil(H*W/256), 2C, B)
+__global__ void __launch_bounds__(256) concat_bwd_scalar_kernel(const float* __restrict__ gvol,
+                                                                float* __restrict__ gL, float* __restrict__ gR,
+                                                                int C, int H, int W, int Dq) {
+    const int hw = blockIdx.x * 256 + threadIdx.x;
+    if (hw >= H * W) return;
+    const int oc = blockIdx.y, b = blockIdx.z;
+    const bool right = oc >= C;
+    float* gout = right ? gR : gL;
+    if (gout == nullptr) return;
+    const int c = right ? oc - C : oc;
+    const int x = hw % W;
+    const size_t HW = (size_t)H * W;
+    const float* g = gvol + ((size_t)b * 2 * C + oc) * Dq * HW + hw;
+    float acc = 0.f;
+    if (right) {
+        const int lim = min(Dq, W - x);
+        for (int i = 0; i < lim; ++i) acc += ld_stream(g + (size_t)i * HW + i);
+    } else {
+        const int lim = min(Dq, x + 1);
+        for (int i = 0; i < lim; ++i) acc += ld_stream(g + (size_t)i * HW);
+    }
+    gout[((size_t)b * C + c) * HW + hw] = acc;
+}
+
+}  // namespace az
+
+using namespace az;
+
+extern "C" int az_concat_volume_fwd(const float* L, const float* R, float* vol, int64_t B, int64_t C, int64_t H,
+                                    int64_t W, int64_t Dq, void* stream) {
+    if (!L || !R || !vol || B <= 0 || C <= 0 || H <= 0 || W <= 0 || Dq <= 0) return AZ_ERR_BAD_ARG;
+    if (H * W >= (1ll << 31) / 4 || B * 2 * C > 65535 * 32) return AZ_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (W % 4 == 0) && aligned16(L) && aligned16(R) && aligned16(vol) && B <= 65535 && 2 * C <= 65535;
+    if (vec) {
+        const int W4 = (int)(W / 4);
+        const int P = kFwdThreads * kFwdPPT;
+        const int pad = (int)((Dq + 3) / 4 * 4);
+        const int rows_cap = (P + W4 - 1) / W4 + 1;
+        const size_t smem = (size_t)4 * rows_cap * (pad + W) * sizeof(float);
+        if (smem <= 200 * 1024) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaError_t e = cudaFuncSetAttribute(concat_fwd_vec4_kernel,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                if (e != cudaSuccess) return (int)e;
+                attr_done = true;
+            }
+            dim3 grid((unsigned)ceil_div(H * W4, P), (unsigned)(2 * C), (unsigned)B);
+            concat_fwd_vec4_kernel<<<grid, kFwdThreads, smem, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq, pad,
+                                                                   rows_cap);
+            AZ_LAUNCH_CHECK();
+            return 0;
+        }
+    }
+    if (Dq > 65535 || B * 2 * C > 65535) return AZ_ERR_BAD_ARG;
+    dim3 grid((unsigned)ceil_div(H * W, 256), (unsigned)Dq, (unsigned)(B * 2 * C));
+    concat_fwd_scalar_kernel<<<grid, 256, 0, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int az_concat_volume_bwd(const float* gvol, float* gL, float* gR, int64_t B, int64_t C, int64_t H,
+                                    int64_t W, int64_t Dq, void* stream) {
+    if (!gvol || B <= 0 || C <= 0 || H <= 0 || W <= 0 || Dq <= 0) return AZ_ERR_BAD_ARG;
+    if (H * W >= (1ll << 31) / 4 || B > 65535 || 2 * C > 65535) return AZ_ERR_BAD_ARG;
+    if (!gL && !gR) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (W % 4 == 0) && aligned16(gvol) && W <= 4 * kBwdThreads;
+    if (vec) {
+        // rows per tile: as many as 4*256 outputs allow, capped so a full-Dq slab fits ~96 KB
+        // (two CTAs per SM) when possible.
+        int ny = (int)((4 * kBwdThreads) / W);
+        if (ny > H) ny = (int)H;
+        const size_t budget = 96 * 1024;
+        while (ny > 1 && (size_t)ny * W * 4 * Dq > budget) --ny;
+        const size_t slab_bytes = (size_t)ny * W * sizeof(float);
+        int chunk = (int)Dq;
+        const size_t hard = 200 * 1024;
+        if (slab_bytes * chunk > budget) {
+            chunk = (int)(budget / slab_bytes);
+            if (chunk < kBwdGroup) chunk = (int)((hard / slab_bytes) < (size_t)Dq ? (hard / slab_bytes) : Dq);
+        }
+        if (chunk >= 1) {
+            const int ngroups = (chunk + kBwdGroup - 1) / kBwdGroup;
+            const size_t smem = slab_bytes * chunk + (size_t)ngroups * sizeof(uint64_t);
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaError_t e = cudaFuncSetAttribute(concat_bwd_bulk_kernel,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+                if (e != cudaSuccess) return (int)e;
+                attr_done = true;
+            }
+            dim3 grid((unsigned)ceil_div(H, ny), (unsigned)(2 * C), (unsigned)B);
+            concat_bwd_bulk_kernel<<<grid, kBwdThreads, smem, st>>>(gvol, gL, gR, (int)C, (int)H, (int)W, (int)Dq, ny,
+                                                                   chunk);
+            AZ_LAUNCH_CHECK();
+            return 0;
+        }
+    }
+    dim3 grid((unsigned)ceil_div(H * W, 256), (unsigned)(2 * C), (unsigned)B);
+    concat_bwd_scalar_kernel<<<grid, 256, 0, st>>>(gvol, gL, gR, (int)C, (int)H, (int)W, (int)Dq);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,204 @@
+// Temporal IR pattern extraction and local contrast normalisation
+// (SURVEY.md §8a rows a11, a12).
+// Reference: /root/reference/tools/temporal_ir.py:35-40 (get_smoothed_ir_pattern), :93-114
+// (per-pixel regression over the frame stack, normalise, threshold) and
+// /root/reference/utils/reprojection.py:175-200 (local_contrast_norm).
+//
+// a11 runs in float64 like numpy (uint8 frames are promoted).  Three launches:
+//   1. slope/diff per pixel + per-image min/max (positive doubles order like uint64 => integer
+//      atomicMin/atomicMax, deterministic);
+//   2. tiled ks x ks box blur of the min-max-normalised diff with BORDER_REFLECT_101 (what
+//      cv2.blur uses by default), threshold.
+// cv2 builds the box sum with running row/column sums whose rounding differs from a direct sum at
+// the 1e-16 level; pixels whose margin to the threshold is below 1e-6 are outside the parity gate.
+#include "common.cuh"
+
+namespace az {
+
+// workspace layout per image b: diff[H*W] doubles, then (after all images) minmax[2*B] as uint64 bit patterns
+__global__ void __launch_bounds__(256) tir_init_kernel(unsigned long long* __restrict__ minmax, int B) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t < B) {
+        minmax[2 * t] = 0x7FF0000000000000ull;  // +inf
+        minmax[2 * t + 1] = 0ull;               // +0.0
+    }
+}
+
+// grid = (ceil(H*W/256), B)
+__global__ void __launch_bounds__(256) tir_slope_kernel(const uint8_t* __restrict__ frames, double* __restrict__ diff,
+                                                        unsigned long long* __restrict__ minmax, int T, int64_t HW) {
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int b = blockIdx.y;
+    double v = 0.0;
+    const bool on = p < HW;
+    if (on) {
+        const uint8_t* f = frames + (size_t)b * T * HW + p;
+        // temporal_ir.py:94-107, numpy float64 op order (no FMA contraction)
+        const double t_avg = (double)((T - 1) * T / 2) / (double)T;  // np.average of the int ramp
+        double ysum = 0.0;
+        for (int t = 0; t < T; ++t) ysum += (double)f[(size_t)t * HW];   // exact (integers)
+        const double y_avg = ysum / (double)T;
+        double num = 0.0, den = 0.0;
+        for (int t = 0; t < T; ++t) {
+            const double dt = (double)t - t_avg;
+            num = __dadd_rn(num, __dmul_rn((double)f[(size_t)t * HW] - y_avg, dt));
+            den = __dadd_rn(den, __dmul_rn(dt, dt));
+        }
+        const double slope = num / den;
+        const double icpt = __dsub_rn(y_avg, __dmul_rn(slope, t_avg));
+        const double first = __dadd_rn(__dmul_rn(slope, 0.0), icpt);
+        const double last = __dadd_rn(__dmul_rn(slope, (double)(T - 1)), icpt);
+        v = fabs(__dsub_rn(last, first) / 255.0);   // :110-111
+        diff[(size_t)b * HW + p] = v;
+    }
+    // block min / max, then one integer atomic each
+    double mn = on ? v : __longlong_as_double(0x7FF0000000000000ll), mx = on ? v : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&minmax[2 * b], (unsigned long long)__double_as_longlong(mn));
+        atomicMax(&minmax[2 * b + 1], (unsigned long long)__double_as_longlong(mx));
+    }
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    // BORDER_REFLECT_101: gfedcb|abcdefgh|gfedcba ; n == 1 degenerates to 0
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        else i = 2 * n - 2 - i;
+    }
+    return i;
+}
+
+constexpr int kTirTX = 32, kTirTY = 8;
+
+// grid = (ceil(W/32), ceil(H/8), B); smem tile (8+ks-1) x (32+ks-1) doubles + row sums
+__global__ void __launch_bounds__(kTirTX * kTirTY) tir_pattern_kernel(const double* __restrict__ diff,
+                                                                     const unsigned long long* __restrict__ minmax,
+                                                                     float* __restrict__ pattern, int H, int W, int ks,
+                                                                     double threshold) {
+    extern __shared__ double tile[];
+    const int h = ks >> 1;
+    const int TW = kTirTX + ks - 1, TH = kTirTY + ks - 1;
+    double* rows = tile + TW * TH;  // [TH][kTirTX] horizontal window sums
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * kTirTX, y0 = blockIdx.y * kTirTY;
+    const double mn = __longlong_as_double((long long)minmax[2 * b]);
+    const double mx = __longlong_as_double((long long)minmax[2 * b + 1]);
+    const double range = __dsub_rn(mx, mn);
+    const double* d = diff + (size_t)b * H * W;
+    const int tid = threadIdx.y * kTirTX + threadIdx.x;
+    for (int t = tid; t < TW * TH; t += kTirTX * kTirTY) {
+        const int ty = t / TW, tx = t - ty * TW;
+        const int yy = reflect101(y0 + ty - h, H), xx = reflect101(x0 + tx - h, W);
+        tile[t] = fabs(__dsub_rn(d[(size_t)yy * W + xx], mn) / range);  // :113 normalise, :36 abs
+    }
+    __syncthreads();
+    for (int t = tid; t < TH * kTirTX; t += kTirTX * kTirTY) {
+        const int ty = t / kTirTX, tx = t - ty * kTirTX;
+        double s = 0.0;
+        for (int k = 0; k < ks; ++k) s += tile[ty * TW + tx + k];
+        rows[t] = s;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x < W && y < H) {
+        double s = 0.0;
+        for (int k = 0; k < ks; ++k) s += rows[(threadIdx.y + k) * kTirTX + threadIdx.x];
+        const double blur = __dmul_rn(s, 1.0 / (double)(ks * ks));
+        const double v = tile[(threadIdx.y + h) * TW + threadIdx.x + h];
+        pattern[(size_t)b * H * W + (size_t)y * W + x] = (__dsub_rn(v, blur) > threshold) ? 1.0f : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// a12 LCN.  grid = (ceil(W/32), ceil(H/8), B); smem tile (8+ks-1) x (32+ks-1) floats, zero padded.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTirTX * kTirTY) lcn_kernel(const float* __restrict__ image,
+                                                             float* __restrict__ normed, float* __restrict__ stdo,
+                                                             int Cin, int H, int W, int ks, float eps) {
+    extern __shared__ float ftile[];
+    const int h = ks >> 1;
+    const int TW = kTirTX + ks - 1, TH = kTirTY + ks - 1;
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * kTirTX, y0 = blockIdx.y * kTirTY;
+    const float* im = image + (size_t)b * Cin * H * W;  // channel 0 (reprojection.py:184-185)
+    const int tid = threadIdx.y * kTirTX + threadIdx.x;
+    for (int t = tid; t < TW * TH; t += kTirTX * kTirTY) {
+        const int ty = t / TW, tx = t - ty * TW;
+        const int yy = y0 + ty - h, xx = x0 + tx - h;
+        ftile[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + (size_t)yy * W + xx) : 0.f;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x < W && y < H) {
+        const float inv = 1.0f / (float)(ks * ks);
+        float s = 0.f;
+        for (int ky = 0; ky < ks; ++ky)
+            for (int kx = 0; kx < ks; ++kx) s += ftile[(threadIdx.y + ky) * TW + threadIdx.x + kx];
+        const float mean = s * inv;
+        float q = 0.f;
+        for (int ky = 0; ky < ks; ++ky)
+            for (int kx = 0; kx < ks; ++kx) {
+                const float t = ftile[(threadIdx.y + ky) * TW + threadIdx.x + kx] - mean;
+                q = fmaf(t, t, q);
+            }
+        const float sd = sqrtf(q * inv);  // population std (unbiased=False, :193-197)
+        const float v = ftile[(threadIdx.y + h) * TW + threadIdx.x + h];
+        const size_t o = (size_t)b * H * W + (size_t)y * W + x;
+        normed[o] = (v - mean) / (sd + eps);
+        stdo[o] = sd;
+    }
+}
+
+}  // namespace az
+
+using namespace az;
+
+extern "C" int64_t az_temporal_ir_workspace_bytes(int64_t B, int64_t H, int64_t W) {
+    return (B * H * W + 2 * B) * (int64_t)sizeof(double);
+}
+
+extern "C" int az_temporal_ir(const uint8_t* frames, float* pattern, void* workspace, int64_t B, int64_t T, int64_t H,
+                              int64_t W, int64_t ks, double threshold, void* stream) {
+    if (!frames || !pattern || !workspace || B <= 0 || T < 2 || H <= 0 || W <= 0 || ks < 1 || (ks % 2) == 0)
+        return AZ_ERR_BAD_ARG;
+    if (B > 65535 || H * W >= (1ll << 31) || ks > 63) return AZ_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* diff = (double*)workspace;
+    unsigned long long* minmax = (unsigned long long*)(diff + B * H * W);
+    const int64_t HW = H * W;
+    tir_init_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(minmax, (int)B);
+    AZ_LAUNCH_CHECK();
+    dim3 g1((unsigned)ceil_div(HW, 256), (unsigned)B);
+    tir_slope_kernel<<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
+    AZ_LAUNCH_CHECK();
+    const int TW = kTirTX + (int)ks - 1, TH = kTirTY + (int)ks - 1;
+    const size_t smem = ((size_t)TW * TH + (size_t)TH * kTirTX) * sizeof(double);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(tir_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 g2((unsigned)ceil_div(W, kTirTX), (unsigned)ceil_div(H, kTirTY), (unsigned)B);
+    tir_pattern_kernel<<<g2, dim3(kTirTX, kTirTY), smem, st>>>(diff, minmax, pattern, (int)H, (int)W, (int)ks, threshold);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int az_local_contrast_norm(const float* image, float* normed, float* stdo, int64_t B, int64_t Cin, int64_t H,
+                                      int64_t W, int64_t ks, float eps, void* stream) {
+    if (!image || !normed || !stdo || B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || ks < 1 || (ks % 2) == 0 || ks > 63)
+        return AZ_ERR_BAD_ARG;
+    if (B > 65535 || H * W >= (1ll << 31)) return AZ_ERR_BAD_ARG;
+    const int TW = kTirTX + (int)ks - 1, TH = kTirTY + (int)ks - 1;
+    const size_t smem = (size_t)TW * TH * sizeof(float);
+    dim3 grid((unsigned)ceil_div(W, kTirTX), (unsigned)ceil_div(H, kTirTY), (unsigned)B);
+    lcn_kernel<<<grid, dim3(kTirTX, kTirTY), smem, (cudaStream_t)stream>>>(image, normed, stdo, (int)Cin, (int)H, (int)W,
+                                                                          (int)ks, eps);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}

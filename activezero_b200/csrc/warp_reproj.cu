@@ -1,0 +1,405 @@
+// Bilinear disparity warp and the fused warp + masked-MSE reprojection losses
+// (SURVEY.md §8a rows a6, a7, a8).
+// Reference: /root/reference/utils/reprojection.py:13-35 (apply_disparity), :81-96
+// (get_reprojection_error_old), :99-127 (get_reproj_error_patch).
+//
+// The sample position follows the reference's fp32 op order (common.cuh: sample_pos), the
+// stand-alone warp follows torch's corner order/FMA chain so it is bit-identical to the CPU
+// oracle; the fused losses never materialise the unfolded / warped [B,C*ps*ps,H,W] tensors:
+// one CTA owns one output row, builds the 11 (ps) vertically-interpolated source rows and the
+// ps target rows in shared memory (zero borders folded into a padded layout, so the tap loop
+// has no bounds checks), and each thread walks the ps x ps taps of its pixels accumulating the
+// squared residual and d(residual)/d(xs).  The kernels are shared-memory/issue bound, not
+// HBM bound (compulsory traffic is ~4 image planes) -- see DESIGN.md.
+#include "common.cuh"
+
+namespace az {
+
+struct Axis {
+    int i0;      // floor(pos), clamped to [-2, size] so it is safe to form indices from
+    float w, e;  // w = pos - floor(pos), e = 1 - w
+    bool v0, v1; // corner i0 / i0+1 inside [0,size)
+};
+
+__device__ __forceinline__ Axis make_axis(float pos, int size) {
+    Axis a;
+    const float fl = floorf(pos);
+    a.w = __fsub_rn(pos, fl);
+    a.e = __fsub_rn(1.0f, a.w);
+    a.v0 = (fl >= 0.0f) && (fl <= (float)(size - 1));
+    a.v1 = (fl >= -1.0f) && (fl <= (float)(size - 2));
+    a.i0 = (int)fminf(fmaxf(fl, -2.0f), (float)size);
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------
+// a6 forward: out[b,c,i,j].  grid = (ceil(W/256), H, B)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ disp,
+                                                       const float* __restrict__ lin_x,
+                                                       const float* __restrict__ lin_y, float* __restrict__ out,
+                                                       int C, int H, int W) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= W) return;
+    const int i = blockIdx.y, b = blockIdx.z;
+    const size_t HW = (size_t)H * W;
+    const float d = disp[(size_t)b * HW + (size_t)i * W + j];
+    const Axis ax = make_axis(sample_pos(__ldg(lin_x + j), __fdiv_rn(d, (float)W), (float)W), W);
+    const Axis ay = make_axis(sample_pos(__ldg(lin_y + i), 0.0f, (float)H), H);
+    const float nw = __fmul_rn(ax.e, ay.e), ne = __fmul_rn(ax.w, ay.e);
+    const float sw = __fmul_rn(ax.e, ay.w), se = __fmul_rn(ax.w, ay.w);
+    const bool m00 = ax.v0 && ay.v0, m01 = ax.v1 && ay.v0, m10 = ax.v0 && ay.v1, m11 = ax.v1 && ay.v1;
+    const size_t o00 = (size_t)ay.i0 * W + ax.i0;
+    for (int c = 0; c < C; ++c) {
+        const float* p = img + ((size_t)b * C + c) * HW;
+        const float v00 = m00 ? __ldg(p + o00) : 0.f, v01 = m01 ? __ldg(p + o00 + 1) : 0.f;
+        const float v10 = m10 ? __ldg(p + o00 + W) : 0.f, v11 = m11 ? __ldg(p + o00 + W + 1) : 0.f;
+        float acc = __fmul_rn(v00, nw);
+        acc = __fmaf_rn(v01, ne, acc);
+        acc = __fmaf_rn(v10, sw, acc);
+        acc = __fmaf_rn(v11, se, acc);
+        out[((size_t)b * C + c) * HW + (size_t)i * W + j] = acc;
+    }
+}
+
+// a6 backward.  gdisp written; gimg accumulated with atomics (zero-filled by the caller).
+__global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__ img, const float* __restrict__ disp,
+                                                       const float* __restrict__ lin_x,
+                                                       const float* __restrict__ lin_y,
+                                                       const float* __restrict__ gout, float* __restrict__ gimg,
+                                                       float* __restrict__ gdisp, int C, int H, int W) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= W) return;
+    const int i = blockIdx.y, b = blockIdx.z;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)i * W + j;
+    const float d = disp[(size_t)b * HW + pix];
+    const Axis ax = make_axis(sample_pos(__ldg(lin_x + j), __fdiv_rn(d, (float)W), (float)W), W);
+    const Axis ay = make_axis(sample_pos(__ldg(lin_y + i), 0.0f, (float)H), H);
+    const float nw = ax.e * ay.e, ne = ax.w * ay.e, sw = ax.e * ay.w, se = ax.w * ay.w;
+    const bool m00 = ax.v0 && ay.v0, m01 = ax.v1 && ay.v0, m10 = ax.v0 && ay.v1, m11 = ax.v1 && ay.v1;
+    const size_t o00 = (size_t)ay.i0 * W + ax.i0;
+    float gix = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const size_t base = ((size_t)b * C + c) * HW;
+        const float g = gout[base + pix];
+        if (gdisp != nullptr) {
+            const float* p = img + base;
+            const float v00 = m00 ? __ldg(p + o00) : 0.f, v01 = m01 ? __ldg(p + o00 + 1) : 0.f;
+            const float v10 = m10 ? __ldg(p + o00 + W) : 0.f, v11 = m11 ? __ldg(p + o00 + W + 1) : 0.f;
+            gix += g * (ay.e * (v01 - v00) + ay.w * (v11 - v10));
+        }
+        if (gimg != nullptr) {
+            float* q = gimg + base;
+            if (m00) atomicAdd(q + o00, nw * g);
+            if (m01) atomicAdd(q + o00 + 1, ne * g);
+            if (m10) atomicAdd(q + o00 + W, sw * g);
+            if (m11) atomicAdd(q + o00 + W + 1, se * g);
+        }
+    }
+    if (gdisp != nullptr) {
+        // chain of grid_sample's unnormalise (x W/2), `2*flow-1` (x 2) and `disp/width` (/ W)
+        gdisp[(size_t)b * HW + pix] = ((gix * (0.5f * (float)W)) * 2.0f) / (float)W;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// a7/a8 fused loss.  grid = (H, B); one CTA per output row; dynamic smem:
+//   Rs[ps][Wp] | Ls[ps][Wp]   (Wp = W + 2*(p+1), data starts at column OFF = p+1)
+// ------------------------------------------------------------------------------------------
+constexpr int kLossThreads = 512;
+
+template <int PS>
+__device__ __forceinline__ void patch_taps(const float* __restrict__ rs, const float* __restrict__ ls, int Wp, int ps,
+                                           float bx0, float bx1, float gx0, float gx1, float& acc, float& gacc) {
+    const int n = PS > 0 ? PS : ps;
+    float a0 = 0.f, a1 = 0.f, g0 = 0.f, g1 = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < n; ++ky) {
+        const float* rr = rs + ky * Wp;
+        const float* ll = ls + ky * Wp;
+        float prev = rr[0];
+#pragma unroll
+        for (int kx = 0; kx < n; ++kx) {
+            const float nxt = rr[kx + 1];
+            const float wu = fmaf(bx1, nxt, bx0 * prev);
+            const float dwu = fmaf(gx1, nxt, -gx0 * prev);
+            const float r = wu - ll[kx];
+            if (kx & 1) { a1 = fmaf(r, r, a1); g1 = fmaf(r, dwu, g1); }
+            else        { a0 = fmaf(r, r, a0); g0 = fmaf(r, dwu, g0); }
+            prev = nxt;
+        }
+    }
+    acc = a0 + a1;
+    gacc = g0 + g1;
+}
+
+template <int PS>
+__global__ void __launch_bounds__(kLossThreads) reproj_loss_kernel(
+    const float* __restrict__ tgt, const float* __restrict__ src, const float* __restrict__ disp, float sign,
+    const uint8_t* __restrict__ mask, const float* __restrict__ lin_x, const float* __restrict__ lin_y, int ps,
+    float* __restrict__ warped, float* __restrict__ gpre, double* __restrict__ partial, int C, int H, int W) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ double red[32];
+    const int i = blockIdx.x, b = blockIdx.y;
+    const int p = (ps - 1) >> 1, OFF = p + 1, Wp = W + 2 * OFF;
+    float* Rs = sm;
+    float* Ls = sm + (size_t)ps * Wp;
+    const size_t HW = (size_t)H * W;
+    const size_t rowbase = (size_t)b * HW + (size_t)i * W;
+
+    const Axis ay = make_axis(sample_pos(__ldg(lin_y + i), 0.0f, (float)H), H);
+    const float ay0 = ay.v0 ? ay.e : 0.f, ay1 = ay.v1 ? ay.w : 0.f;
+    const bool want_warped = (warped != nullptr) && (ps == 1);
+
+    double tot = 0.0, cnt = 0.0;
+    for (int c = 0; c < C; ++c) {
+        const float* sp = src + ((size_t)b * C + c) * HW;
+        const float* tp = tgt + ((size_t)b * C + c) * HW;
+        __syncthreads();  // the previous channel's taps are done with the shared rows
+        for (int xx = threadIdx.x; xx < Wp; xx += kLossThreads) {
+            const int x = xx - OFF;
+            const bool inx = (x >= 0) && (x < W);
+            // source rows y0-p .. y0+1+p, blended pairwise with the (validity-folded) row weights
+            int yy = ay.i0 - p;
+            float prev = (inx && yy >= 0 && yy < H) ? __ldg(sp + (size_t)yy * W + x) : 0.f;
+            for (int ky = 0; ky < ps; ++ky) {
+                ++yy;
+                const float nxt = (inx && yy >= 0 && yy < H) ? __ldg(sp + (size_t)yy * W + x) : 0.f;
+                Rs[ky * Wp + xx] = fmaf(ay1, nxt, ay0 * prev);
+                prev = nxt;
+                const int ty = i + ky - p;
+                Ls[ky * Wp + xx] = (inx && ty >= 0 && ty < H) ? __ldg(tp + (size_t)ty * W + x) : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int j = threadIdx.x; j < W; j += kLossThreads) {
+            const bool m = mask == nullptr ? true : (mask[rowbase + j] != 0);
+            float a = 0.f, g = 0.f;
+            if (m || want_warped) {
+                const float d = sign * disp[rowbase + j];
+                const Axis ax = make_axis(sample_pos(__ldg(lin_x + j), __fdiv_rn(d, (float)W), (float)W), W);
+                const int x0 = min(max(ax.i0, -1), W - 1);  // outside this range both corners are invalid
+                const float bx0 = ax.v0 ? ax.e : 0.f, bx1 = ax.v1 ? ax.w : 0.f;
+                const float* rs = Rs + OFF + x0 - p;
+                if (m)
+                    patch_taps<PS>(rs, Ls + (OFF + j - p), Wp, ps, bx0, bx1, ax.v0 ? 1.f : 0.f, ax.v1 ? 1.f : 0.f, a, g);
+                if (want_warped)  // ps == 1: the single tap *is* the warped pixel (the mask does not apply to it)
+                    warped[((size_t)b * C + c) * HW + (size_t)i * W + j] = fmaf(bx1, rs[1], bx0 * rs[0]);
+            }
+            tot += (double)a;
+            if (c == 0 && m) cnt += 1.0;
+            if (gpre != nullptr) gpre[rowbase + j] = (c == 0 ? 0.f : gpre[rowbase + j]) + g;
+        }
+    }
+    const double bs = block_sum(tot, red);
+    const double bc = block_sum(cnt, red);
+    if (threadIdx.x == 0) {
+        const size_t r = (size_t)b * H + i;
+        partial[2 * r] = bs;
+        partial[2 * r + 1] = bc;
+    }
+}
+
+// final reduction of the per-row partials, fixed order => deterministic.  1 CTA.
+__global__ void __launch_bounds__(1024) reproj_finalize_kernel(const double* __restrict__ partial, int64_t n, double K,
+                                                               float* __restrict__ loss_out,
+                                                               double* __restrict__ stats) {
+    __shared__ double red[32];
+    double s = 0.0, c = 0.0;
+    for (int64_t r = threadIdx.x; r < n; r += 1024) { s += partial[2 * r]; c += partial[2 * r + 1]; }
+    s = block_sum(s, red);
+    c = block_sum(c, red);
+    if (threadIdx.x == 0) {
+        stats[0] = s;
+        stats[1] = c;
+        loss_out[0] = (float)(s / (K * c));  // 0/0 = NaN for an empty mask, like F.mse_loss of nothing
+    }
+}
+
+__global__ void __launch_bounds__(256) reproj_bwd_kernel(const float* __restrict__ gpre, const double* __restrict__ stats,
+                                                         const float* __restrict__ gloss, float sign, double K,
+                                                         float* __restrict__ gdisp, int64_t n) {
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= n) return;
+    const float scale = (float)((double)gloss[0] * (double)sign * 2.0 / (K * stats[1]));
+    gdisp[t] = scale * gpre[t];
+}
+
+// ------------------------------------------------------------------------------------------
+// Fold (overlap-sum) of the warped unfolded planes, cropped: reprojection.py:120-125.
+// vis[b,c,y,x] = sum_{ky,kx} Wu[(c,ky,kx)][y+p-ky, x+p-kx].   grid = (H, C, B)
+// smem: Bk[ps][Wp] blended source rows | XS[ps][W] sample x of source row i = y+p-ky
+// ------------------------------------------------------------------------------------------
+constexpr int kFoldThreads = 512;
+
+__global__ void __launch_bounds__(kFoldThreads) patch_fold_kernel(const float* __restrict__ src,
+                                                                 const float* __restrict__ disp, float sign,
+                                                                 const float* __restrict__ lin_x,
+                                                                 const float* __restrict__ lin_y, int ps,
+                                                                 float* __restrict__ vis, int C, int H, int W) {
+    extern __shared__ __align__(16) float sm[];
+    const int y = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
+    const int p = (ps - 1) >> 1, OFF = p + 1, Wp = W + 2 * OFF;
+    float* Bk = sm;
+    float* XS = sm + (size_t)ps * Wp;
+    const size_t HW = (size_t)H * W;
+    const float* sp = src + ((size_t)b * C + c) * HW;
+    const float* dp = disp + (size_t)b * HW;
+
+    for (int ky = 0; ky < ps; ++ky) {
+        const int i = y + p - ky;  // source (unfolded-plane) row contributing through tap row ky
+        const bool rowok = (i >= 0) && (i < H);
+        float ay0 = 0.f, ay1 = 0.f;
+        int r0 = 0;
+        if (rowok) {
+            const Axis ay = make_axis(sample_pos(__ldg(lin_y + i), 0.0f, (float)H), H);
+            ay0 = ay.v0 ? ay.e : 0.f;
+            ay1 = ay.v1 ? ay.w : 0.f;
+            r0 = ay.i0 + ky - p;  // image row read by corner y0 of tap row ky
+        }
+        for (int xx = threadIdx.x; xx < Wp; xx += kFoldThreads) {
+            const int x = xx - OFF;
+            float v = 0.f;
+            if (rowok && x >= 0 && x < W) {
+                const float a = (r0 >= 0 && r0 < H) ? __ldg(sp + (size_t)r0 * W + x) : 0.f;
+                const float bb = (r0 + 1 >= 0 && r0 + 1 < H) ? __ldg(sp + (size_t)(r0 + 1) * W + x) : 0.f;
+                v = fmaf(ay1, bb, ay0 * a);
+            }
+            Bk[ky * Wp + xx] = v;
+        }
+        for (int j = threadIdx.x; j < W; j += kFoldThreads) {
+            float xs = -8.0f;  // floor = -8: both corners invalid
+            if (rowok) xs = sample_pos(__ldg(lin_x + j), __fdiv_rn(sign * dp[(size_t)i * W + j], (float)W), (float)W);
+            XS[ky * W + j] = xs;
+        }
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < W; x += kFoldThreads) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int ky = 0; ky < ps; ++ky) {
+            const float* bk = Bk + ky * Wp + OFF;
+            const float* xs = XS + ky * W;
+            for (int kx = 0; kx < ps; ++kx) {
+                const int j = x + p - kx;
+                if (j < 0 || j >= W) continue;
+                const Axis ax = make_axis(xs[j], W);
+                const int x0 = min(max(ax.i0, -1), W - 1) + kx - p;
+                const float t = fmaf(ax.v1 ? ax.w : 0.f, bk[x0 + 1], (ax.v0 ? ax.e : 0.f) * bk[x0]);
+                if (kx & 1) a1 += t; else a0 += t;
+            }
+        }
+        vis[((size_t)b * C + c) * HW + (size_t)y * W + x] = a0 + a1;
+    }
+}
+
+}  // namespace az
+
+using namespace az;
+
+extern "C" int az_warp_fwd(const float* img, const float* disp, const float* lin_x, const float* lin_y, float* out,
+                           int64_t B, int64_t C, int64_t H, int64_t W, void* stream) {
+    if (!img || !disp || !lin_x || !lin_y || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return AZ_ERR_BAD_ARG;
+    if (H > 65535 || B > 65535 || H * W >= (1ll << 31)) return AZ_ERR_BAD_ARG;
+    dim3 grid((unsigned)ceil_div(W, 256), (unsigned)H, (unsigned)B);
+    warp_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, disp, lin_x, lin_y, out, (int)C, (int)H, (int)W);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int az_warp_bwd(const float* img, const float* disp, const float* lin_x, const float* lin_y,
+                           const float* gout, float* gimg, float* gdisp, int64_t B, int64_t C, int64_t H, int64_t W,
+                           void* stream) {
+    if (!img || !disp || !lin_x || !lin_y || !gout || B <= 0 || C <= 0 || H <= 0 || W <= 0) return AZ_ERR_BAD_ARG;
+    if (H > 65535 || B > 65535 || H * W >= (1ll << 31)) return AZ_ERR_BAD_ARG;
+    if (!gimg && !gdisp) return 0;
+    dim3 grid((unsigned)ceil_div(W, 256), (unsigned)H, (unsigned)B);
+    warp_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, disp, lin_x, lin_y, gout, gimg, gdisp, (int)C, (int)H,
+                                                           (int)W);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t az_reproj_workspace_bytes(int64_t B, int64_t H) { return B * H * 2 * (int64_t)sizeof(double); }
+
+template <int PS>
+static int launch_loss(const float* tgt, const float* src, const float* disp, float sign, const uint8_t* mask,
+                       const float* lin_x, const float* lin_y, int ps, float* warped, float* gpre, double* partial,
+                       int B, int C, int H, int W, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(reproj_loss_kernel<PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(220 * 1024));
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)H, (unsigned)B);
+    reproj_loss_kernel<PS><<<grid, kLossThreads, smem, st>>>(tgt, src, disp, sign, mask, lin_x, lin_y, ps, warped, gpre,
+                                                            partial, C, H, W);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int az_reproj_loss_fwd(const float* tgt, const float* src, const float* disp, float sign,
+                                  const uint8_t* mask, const float* lin_x, const float* lin_y, int64_t ps,
+                                  float* warped, float* gpre, float* loss_out, double* stats, void* workspace,
+                                  int64_t B, int64_t C, int64_t H, int64_t W, void* stream) {
+    if (!tgt || !src || !disp || !lin_x || !lin_y || !loss_out || !stats || !workspace) return AZ_ERR_BAD_ARG;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || ps < 1 || (ps % 2) == 0) return AZ_ERR_BAD_ARG;
+    if (B > 65535 || H * W >= (1ll << 31)) return AZ_ERR_BAD_ARG;
+    if (warped != nullptr && ps != 1) return AZ_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int p = (int)(ps - 1) / 2;
+    const size_t Wp = (size_t)W + 2 * (p + 1);
+    const size_t smem = 2 * (size_t)ps * Wp * sizeof(float);
+    if (smem > 220 * 1024) return AZ_ERR_BAD_ARG;
+    double* partial = (double*)workspace;
+    int rc;
+#define AZ_LOSS_CASE(N)                                                                                              \
+    case N:                                                                                                          \
+        rc = launch_loss<N>(tgt, src, disp, sign, mask, lin_x, lin_y, (int)ps, warped, gpre, partial, (int)B, (int)C, \
+                            (int)H, (int)W, smem, st);                                                               \
+        break;
+    switch (ps) {
+        AZ_LOSS_CASE(1)
+        AZ_LOSS_CASE(3)
+        AZ_LOSS_CASE(5)
+        AZ_LOSS_CASE(7)
+        AZ_LOSS_CASE(9)
+        AZ_LOSS_CASE(11)
+        default:
+            rc = launch_loss<0>(tgt, src, disp, sign, mask, lin_x, lin_y, (int)ps, warped, gpre, partial, (int)B, (int)C,
+                                (int)H, (int)W, smem, st);
+    }
+#undef AZ_LOSS_CASE
+    if (rc != 0) return rc;
+    reproj_finalize_kernel<<<1, 1024, 0, st>>>(partial, B * H, (double)(C * ps * ps), loss_out, stats);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int az_reproj_loss_bwd(const float* gpre, const double* stats, const float* gloss, float sign,
+                                  float* gdisp, int64_t B, int64_t C, int64_t H, int64_t W, int64_t ps,
+                                  void* stream) {
+    if (!gpre || !stats || !gloss || !gdisp || B <= 0 || C <= 0 || H <= 0 || W <= 0 || ps < 1) return AZ_ERR_BAD_ARG;
+    const int64_t n = B * H * W;
+    reproj_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(gpre, stats, gloss, sign,
+                                                                                    (double)(C * ps * ps), gdisp, n);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int az_patch_fold(const float* src, const float* disp, float sign, const float* lin_x, const float* lin_y,
+                             int64_t ps, float* vis, int64_t B, int64_t C, int64_t H, int64_t W, void* stream) {
+    if (!src || !disp || !lin_x || !lin_y || !vis || B <= 0 || C <= 0 || H <= 0 || W <= 0 || ps < 1 || (ps % 2) == 0)
+        return AZ_ERR_BAD_ARG;
+    if (B > 65535 || C > 65535 || H * W >= (1ll << 31)) return AZ_ERR_BAD_ARG;
+    const int p = (int)(ps - 1) / 2;
+    const size_t Wp = (size_t)W + 2 * (p + 1);
+    const size_t smem = (size_t)ps * (Wp + W) * sizeof(float);
+    if (smem > 220 * 1024) return AZ_ERR_BAD_ARG;
+    cudaError_t e = cudaFuncSetAttribute(patch_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(220 * 1024));
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)H, (unsigned)C, (unsigned)B);
+    patch_fold_kernel<<<grid, kFoldThreads, smem, (cudaStream_t)stream>>>(src, disp, sign, lin_x, lin_y, (int)ps, vis,
+                                                                         (int)C, (int)H, (int)W);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,335 @@
+"""PyTorch-facing operators of the B200 stereo hot path.
+
+One ``torch.autograd.Function`` per differentiable op (the pattern the reference
+itself uses for an external CUDA module: ``CorrSampler`` in
+``/root/reference/nets/raft/corr.py:18-31``), each a thin marshalling layer over
+the C ABI in ``include/az_stereo.h``.  PyTorch provides device memory and the
+current stream; all arithmetic happens in ``libaz_stereo.so``.  CUDA float32
+tensors only -- there is no CPU path and no eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+_NULL = ctypes.c_void_p(0)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return _NULL if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (activezero_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name}: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_LIN_CACHE: dict = {}
+
+
+def linspace_table(n: int, device: torch.device) -> torch.Tensor:
+    """``torch.linspace(0, 1, n)`` evaluated on the CPU in fp32 -- the base grid of
+    ``apply_disparity`` (``utils/reprojection.py:18-24``) -- cached on ``device``.
+    The table (not a closed form) is what makes the sample position bit-identical
+    to the reference's."""
+    key = (int(n), str(device))
+    tab = _LIN_CACHE.get(key)
+    if tab is None:
+        tab = torch.linspace(0, 1, int(n), dtype=torch.float32).to(device)
+        _LIN_CACHE[key] = tab
+    return tab
+
+
+# ----------------------------------------------------------------------------
+# a1/a2 concat volume
+# ----------------------------------------------------------------------------
+class ConcatVolumeFn(torch.autograd.Function):
+    """nets/psmnet/psmnet.py:151-165 and its autograd."""
+
+    @staticmethod
+    def forward(ctx, ref_feat, tgt_feat, num_disp: int):
+        L = _cuda_f32(ref_feat, "ref_feat")
+        R = _cuda_f32(tgt_feat, "tgt_feat")
+        if L.shape != R.shape or L.dim() != 4:
+            raise ValueError("concat volume: features must both be [B,C,H,W]")
+        B, C, H, W = L.shape
+        vol = torch.empty((B, 2 * C, int(num_disp), H, W), dtype=torch.float32, device=L.device)
+        with torch.cuda.device(L.device):
+            _lib.call("az_concat_volume_fwd", _ptr(L), _ptr(R), _ptr(vol), B, C, H, W, int(num_disp), _stream())
+        ctx.dims = (B, C, H, W, int(num_disp))
+        return vol
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gvol):
+        B, C, H, W, Dq = ctx.dims
+        g = _cuda_f32(gvol, "grad_volume")
+        gL = torch.empty((B, C, H, W), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[0] else None
+        gR = torch.empty((B, C, H, W), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(g.device):
+            _lib.call("az_concat_volume_bwd", _ptr(g), _ptr(gL), _ptr(gR), B, C, H, W, Dq, _stream())
+        return gL, gR, None
+
+
+def build_concat_volume(ref_feat, tgt_feat, num_disp: int):
+    """[B,C,H,W] x2 -> [B,2C,num_disp,H,W] (replaces psmnet.py:151-165)."""
+    return ConcatVolumeFn.apply(ref_feat, tgt_feat, num_disp)
+
+
+# ----------------------------------------------------------------------------
+# a3 group-wise correlation volume (no reference counterpart)
+# ----------------------------------------------------------------------------
+class GwcVolumeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ref_feat, tgt_feat, num_disp: int, num_groups: int):
+        L = _cuda_f32(ref_feat, "ref_feat")
+        R = _cuda_f32(tgt_feat, "tgt_feat")
+        if L.shape != R.shape or L.dim() != 4:
+            raise ValueError("gwc volume: features must both be [B,C,H,W]")
+        B, C, H, W = L.shape
+        if C % int(num_groups) != 0:
+            raise ValueError("gwc volume: C must be divisible by num_groups")
+        vol = torch.empty((B, int(num_groups), int(num_disp), H, W), dtype=torch.float32, device=L.device)
+        with torch.cuda.device(L.device):
+            _lib.call("az_gwc_volume_fwd", _ptr(L), _ptr(R), _ptr(vol), B, C, H, W, int(num_disp), int(num_groups),
+                      _stream())
+        ctx.save_for_backward(L, R)
+        ctx.dims = (B, C, H, W, int(num_disp), int(num_groups))
+        return vol
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gvol):
+        L, R = ctx.saved_tensors
+        B, C, H, W, Dq, G = ctx.dims
+        g = _cuda_f32(gvol, "grad_volume")
+        gL = torch.empty_like(L) if ctx.needs_input_grad[0] else None
+        gR = torch.empty_like(R) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(g.device):
+            _lib.call("az_gwc_volume_bwd", _ptr(g), _ptr(L), _ptr(R), _ptr(gL), _ptr(gR), B, C, H, W, Dq, G, _stream())
+        return gL, gR, None, None
+
+
+def build_gwc_volume(ref_feat, tgt_feat, num_disp: int, num_groups: int):
+    return GwcVolumeFn.apply(ref_feat, tgt_feat, num_disp, num_groups)
+
+
+# ----------------------------------------------------------------------------
+# a4/a5 soft-argmin
+# ----------------------------------------------------------------------------
+class SoftArgminFn(torch.autograd.Function):
+    """F.softmax(cost, 1) + DisparityRegression (psmnet.py:200-201,
+    psmnet_submodule.py:80-89) fused; takes LOGITS."""
+
+    @staticmethod
+    def forward(ctx, cost):
+        c = _cuda_f32(cost, "cost")
+        if c.dim() != 4:
+            raise ValueError("soft_argmin: cost must be [B,D,H,W]")
+        B, D, H, W = c.shape
+        disp = torch.empty((B, 1, H, W), dtype=torch.float32, device=c.device)
+        need_bwd = ctx.needs_input_grad[0]
+        lse = torch.empty_like(disp) if need_bwd else None
+        with torch.cuda.device(c.device):
+            _lib.call("az_soft_argmin_fwd", _ptr(c), _ptr(disp), _ptr(lse), B, D, H, W, _stream())
+        if need_bwd:
+            ctx.save_for_backward(c, disp, lse)
+        return disp
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gdisp):
+        c, disp, lse = ctx.saved_tensors
+        B, D, H, W = c.shape
+        g = _cuda_f32(gdisp, "grad_disp")
+        gcost = torch.empty_like(c)
+        with torch.cuda.device(c.device):
+            _lib.call("az_soft_argmin_bwd", _ptr(c), _ptr(disp), _ptr(lse), _ptr(g), _ptr(gcost), B, D, H, W, _stream())
+        return gcost
+
+
+def soft_argmin(cost):
+    """[B,D,H,W] logits -> [B,1,H,W] expected disparity."""
+    return SoftArgminFn.apply(cost)
+
+
+# ----------------------------------------------------------------------------
+# a6 bilinear disparity warp
+# ----------------------------------------------------------------------------
+class WarpFn(torch.autograd.Function):
+    """apply_disparity (utils/reprojection.py:13-35)."""
+
+    @staticmethod
+    def forward(ctx, img, disp):
+        im = _cuda_f32(img, "img")
+        d = _cuda_f32(disp, "disp")
+        if im.dim() != 4 or d.dim() != 4 or d.shape[1] != 1 or d.shape[0] != im.shape[0] or d.shape[2:] != im.shape[2:]:
+            raise ValueError("apply_disparity: img [B,C,H,W], disp [B,1,H,W]")
+        B, C, H, W = im.shape
+        out = torch.empty_like(im)
+        lx, ly = linspace_table(W, im.device), linspace_table(H, im.device)
+        with torch.cuda.device(im.device):
+            _lib.call("az_warp_fwd", _ptr(im), _ptr(d), _ptr(lx), _ptr(ly), _ptr(out), B, C, H, W, _stream())
+        ctx.save_for_backward(im, d)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        im, d = ctx.saved_tensors
+        B, C, H, W = im.shape
+        g = _cuda_f32(gout, "grad_out")
+        gimg = torch.zeros_like(im) if ctx.needs_input_grad[0] else None
+        gdisp = torch.empty_like(d) if ctx.needs_input_grad[1] else None
+        lx, ly = linspace_table(W, im.device), linspace_table(H, im.device)
+        with torch.cuda.device(im.device):
+            _lib.call("az_warp_bwd", _ptr(im), _ptr(d), _ptr(lx), _ptr(ly), _ptr(g), _ptr(gimg), _ptr(gdisp),
+                      B, C, H, W, _stream())
+        return gimg, gdisp
+
+
+def warp(img, disp):
+    return WarpFn.apply(img, disp)
+
+
+# ----------------------------------------------------------------------------
+# a7/a8 fused warp + masked MSE
+# ----------------------------------------------------------------------------
+def _mask_u8(mask: Optional[torch.Tensor], like: torch.Tensor) -> Optional[torch.Tensor]:
+    if mask is None:
+        return None
+    if not mask.is_cuda:
+        raise ValueError("mask: expected a CUDA tensor")
+    B, _, H, W = like.shape
+    if mask.dim() != 4 or mask.shape[0] != B or mask.shape[1] != 1 or mask.shape[2] != H or mask.shape[3] != W:
+        raise ValueError("mask must be [B,1,H,W]")
+    m = mask if mask.dtype == torch.bool else (mask != 0)
+    return m.contiguous().view(torch.uint8)
+
+
+class ReprojLossFn(torch.autograd.Function):
+    """Masked MSE between ``tgt`` and ``apply_disparity(unfold(src), sign*disp)``
+    (reprojection.py:81-96 for ps = 1, :99-118 for the patch loss).  Differentiable
+    w.r.t. ``disp`` only (what the trainer needs: the images are data)."""
+
+    @staticmethod
+    def forward(ctx, tgt, src, disp, mask_u8, ps: int, sign: float, want_warped: bool):
+        t = _cuda_f32(tgt, "tgt")
+        s = _cuda_f32(src, "src")
+        d = _cuda_f32(disp, "disp")
+        if t.shape != s.shape or t.dim() != 4 or d.shape != (t.shape[0], 1, t.shape[2], t.shape[3]):
+            raise ValueError("reprojection loss: images [B,C,H,W], disp [B,1,H,W]")
+        B, C, H, W = t.shape
+        dev = t.device
+        need_bwd = ctx.needs_input_grad[2]
+        warped = torch.empty_like(t) if (want_warped and ps == 1) else None
+        gpre = torch.empty_like(d) if need_bwd else None
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        stats = torch.empty((2,), dtype=torch.float64, device=dev)
+        ws = torch.empty((_lib.query("az_reproj_workspace_bytes", B, H),), dtype=torch.uint8, device=dev)
+        lx, ly = linspace_table(W, dev), linspace_table(H, dev)
+        with torch.cuda.device(dev):
+            _lib.call("az_reproj_loss_fwd", _ptr(t), _ptr(s), _ptr(d), float(sign), _ptr(mask_u8), _ptr(lx), _ptr(ly),
+                      int(ps), _ptr(warped), _ptr(gpre), _ptr(loss), _ptr(stats), _ptr(ws), B, C, H, W, _stream())
+        if need_bwd:
+            ctx.save_for_backward(gpre, stats)
+        ctx.meta = (B, C, H, W, int(ps), float(sign))
+        if warped is not None:
+            ctx.mark_non_differentiable(warped)
+        return loss.reshape(()), warped
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gloss, _gwarped):
+        gpre, stats = ctx.saved_tensors
+        B, C, H, W, ps, sign = ctx.meta
+        gl = gloss.reshape(1).to(torch.float32).contiguous()
+        gdisp = torch.empty_like(gpre)
+        with torch.cuda.device(gpre.device):
+            _lib.call("az_reproj_loss_bwd", _ptr(gpre), _ptr(stats), _ptr(gl), sign, _ptr(gdisp), B, C, H, W, ps,
+                      _stream())
+        return None, None, gdisp, None, None, None, None
+
+
+def reproj_loss(tgt, src, disp, mask=None, ps: int = 1, sign: float = -1.0, want_warped: bool = False):
+    """-> (loss 0-dim, warped [B,C,H,W] or None)."""
+    if tgt.requires_grad or src.requires_grad:
+        raise ValueError("reproj_loss is differentiable w.r.t. disp only; use warp() for image gradients")
+    return ReprojLossFn.apply(tgt, src, disp, _mask_u8(mask, tgt), ps, sign, want_warped)
+
+
+def patch_fold(src, disp, ps: int, sign: float = -1.0):
+    """Fold of the warped unfolded planes, cropped (reprojection.py:120-125); no grad."""
+    s = _cuda_f32(src.detach(), "src")
+    d = _cuda_f32(disp.detach(), "disp")
+    B, C, H, W = s.shape
+    vis = torch.empty_like(s)
+    lx, ly = linspace_table(W, s.device), linspace_table(H, s.device)
+    with torch.cuda.device(s.device):
+        _lib.call("az_patch_fold", _ptr(s), _ptr(d), float(sign), _ptr(lx), _ptr(ly), int(ps), _ptr(vis), B, C, H, W,
+                  _stream())
+    return vis
+
+
+# ----------------------------------------------------------------------------
+# a10 scatter warp, a11 temporal IR, a12 LCN (non-differentiable)
+# ----------------------------------------------------------------------------
+def scatter_warp(img, disp, check_sign: bool = True):
+    """apply_disparity_cu (utils/warp_ops.py:55-95).  ``check_sign`` keeps the
+    reference's assertion that the disparities do not mix signs (one 4-byte
+    device->host read instead of the reference's two full reductions)."""
+    assert img.is_contiguous() and disp.is_contiguous()
+    assert img.device.type == disp.device.type == "cuda"
+    assert disp.dtype == torch.int
+    if img.dtype != torch.float32:
+        raise ValueError("apply_disparity_cu: img must be float32")
+    N, C, H, W = img.shape
+    if disp.numel() != N * H * W:
+        raise ValueError("apply_disparity_cu: disp must be [N,H,W] or [N,1,H,W]")
+    out = torch.empty_like(img)
+    flags = torch.zeros((1,), dtype=torch.int32, device=img.device) if check_sign else None
+    with torch.cuda.device(img.device):
+        _lib.call("az_scatter_warp", _ptr(img), _ptr(disp), _ptr(out), _ptr(flags), N, C, H, W, _stream())
+    if check_sign:
+        assert int(flags.item()) != 3, "disparities must be all >= 0 or all <= 0"
+    return out
+
+
+def temporal_ir_pattern(frames, ks: int = 11, threshold: float = 0.005):
+    """[B,T,H,W] or [T,H,W] uint8 -> [B,H,W] / [H,W] float32 {0,1}
+    (tools/temporal_ir.py:93-114)."""
+    if not frames.is_cuda or frames.dtype != torch.uint8:
+        raise ValueError("temporal_ir_pattern: expected a CUDA uint8 tensor")
+    squeeze = frames.dim() == 3
+    f = (frames.unsqueeze(0) if squeeze else frames).contiguous()
+    B, T, H, W = f.shape
+    pat = torch.empty((B, H, W), dtype=torch.float32, device=f.device)
+    ws = torch.empty((_lib.query("az_temporal_ir_workspace_bytes", B, H, W),), dtype=torch.uint8, device=f.device)
+    with torch.cuda.device(f.device):
+        _lib.call("az_temporal_ir", _ptr(f), _ptr(pat), _ptr(ws), B, T, H, W, int(ks), float(threshold), _stream())
+    return pat[0] if squeeze else pat
+
+
+def local_contrast_norm(image, kernel_size: int = 9, eps: float = 1e-5):
+    """utils/reprojection.py:175-200 -> (normed [B,1,H,W], std [B,1,H,W])."""
+    assert kernel_size % 2 == 1, "Kernel size should be odd"
+    im = _cuda_f32(image.detach(), "image")
+    B, Cin, H, W = im.shape
+    normed = torch.empty((B, 1, H, W), dtype=torch.float32, device=im.device)
+    std = torch.empty_like(normed)
+    with torch.cuda.device(im.device):
+        _lib.call("az_local_contrast_norm", _ptr(im), _ptr(normed), _ptr(std), B, Cin, H, W, int(kernel_size),
+                  float(eps), _stream())
+    return normed, std

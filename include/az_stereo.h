@@ -1,0 +1,127 @@
+/* az_stereo.h -- C ABI of libaz_stereo.so: the B200 (sm_100a) implementation of
+ * ActiveZero's stereo-matching hot path.
+ *
+ * Convention (modelled on the reference's own raw-pointer launch convention,
+ * /root/reference/utils/warp_ops.py:79-93: args = data_ptr()s + int dims,
+ * stream = torch.cuda.current_stream().cuda_stream):
+ *   - every pointer is a DEVICE pointer to a dense, contiguous NCHW / NCDHW
+ *     float32 tensor unless the comment says otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; the call only enqueues work
+ *     on it: it never allocates, never frees, never synchronises;
+ *   - the caller owns every buffer (inputs, outputs, workspaces) and keeps it
+ *     alive until the stream has passed the call;
+ *   - the return value is a cudaError_t as int (0 = success); AZ_ERR_* (< 0)
+ *     flags an argument the library rejects before launching anything;
+ *   - stateless and re-entrant; one process per GPU.
+ * All citations are relative to /root/reference.
+ */
+#ifndef AZ_STEREO_H
+#define AZ_STEREO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZ_ERR_BAD_ARG (-1)      /* null pointer / non-positive dim / unsupported size */
+#define AZ_ERR_UNALIGNED (-2)    /* pointer not aligned as the fast path requires (never returned: falls back) */
+
+/* Library / build identification: returns "az_stereo <ver> sm_100a". */
+const char* az_version(void);
+/* Human-readable text for a non-zero return value of any function below. */
+const char* az_error_string(int code);
+
+/* ---- a1/a2: concat cost volume -- nets/psmnet/psmnet.py:151-165 (= psmnet_3.py:149-163) ----
+ * vol[b,c,i,y,x]   = L[b,c,y,x]      (x >= i, else 0),  c in [0,C)
+ * vol[b,C+c,i,y,x] = R[b,c,y,x-i]    (x >= i, else 0)
+ * L,R: [B,C,H,W]; vol: [B,2C,Dq,H,W].  Every element of vol is written (no memset needed). */
+int az_concat_volume_fwd(const float* L, const float* R, float* vol,
+                         int64_t B, int64_t C, int64_t H, int64_t W, int64_t Dq, void* stream);
+/* Autograd of the slice assignments of psmnet.py:158-164 (atomic-free gather):
+ * gL[b,c,y,x] = sum_{i<=min(x,Dq-1)} gvol[b,c,i,y,x];  gR[b,c,y,x] = sum_{i<Dq, x+i<W} gvol[b,C+c,i,y,x+i].
+ * gL / gR may each be NULL (that half is skipped). */
+int az_concat_volume_bwd(const float* gvol, float* gL, float* gR,
+                         int64_t B, int64_t C, int64_t H, int64_t W, int64_t Dq, void* stream);
+
+/* ---- a3: group-wise correlation volume -- NOT IN THE REFERENCE (parity unpinned) ----
+ * vol[b,g,i,y,x] = (1/(C/G)) * sum_{c in group g} L[b,c,y,x]*R[b,c,y,x-i]  (x >= i, else 0); vol: [B,G,Dq,H,W]. */
+int az_gwc_volume_fwd(const float* L, const float* R, float* vol,
+                      int64_t B, int64_t C, int64_t H, int64_t W, int64_t Dq, int64_t G, void* stream);
+int az_gwc_volume_bwd(const float* gvol, const float* L, const float* R, float* gL, float* gR,
+                      int64_t B, int64_t C, int64_t H, int64_t W, int64_t Dq, int64_t G, void* stream);
+
+/* ---- a4/a5: soft-argmin = F.softmax(cost,1) + DisparityRegression --
+ *      nets/psmnet/psmnet.py:200-201,204-205,212-217 + nets/psmnet/psmnet_submodule.py:80-89 ----
+ * disp[b,0,y,x] = sum_d d * softmax_d(cost[b,:,y,x]).  cost: [B,D,H,W] LOGITS; disp: [B,1,H,W];
+ * lse (optional, may be NULL): [B,1,H,W] log-sum-exp saved for the backward. */
+int az_soft_argmin_fwd(const float* cost, float* disp, float* lse,
+                       int64_t B, int64_t D, int64_t H, int64_t W, void* stream);
+/* gcost[b,d,y,x] = exp(cost - lse) * (d - disp) * gdisp[b,0,y,x] */
+int az_soft_argmin_bwd(const float* cost, const float* disp, const float* lse, const float* gdisp, float* gcost,
+                       int64_t B, int64_t D, int64_t H, int64_t W, void* stream);
+
+/* ---- a6: bilinear disparity warp -- utils/reprojection.py:13-35 (apply_disparity) ----
+ * out[b,c,i,j] = bilinear2D(img[b,c]; xs, ys), zeros padding, align_corners=False, with the reference's
+ * fp32 op order: f = lin_x[j] + disp/W; g = 2f-1; xs = ((g+1)*W-1)/2 (same for y with lin_y[i], H).
+ * lin_x [W], lin_y [H]: DEVICE copies of torch.linspace(0,1,n) (reprojection.py:18-24).
+ * img,out: [B,C,H,W]; disp: [B,1,H,W] (already signed: the reference passes -pred_disp_l). */
+int az_warp_fwd(const float* img, const float* disp, const float* lin_x, const float* lin_y, float* out,
+                int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
+/* gdisp [B,1,H,W] (may be NULL) is written; gimg [B,C,H,W] (may be NULL) must be zero-filled by the
+ * caller and is accumulated with float atomics (as torch's grid_sampler backward does). */
+int az_warp_bwd(const float* img, const float* disp, const float* lin_x, const float* lin_y,
+                const float* gout, float* gimg, float* gdisp,
+                int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
+
+/* ---- a7/a8: fused warp + masked-MSE reprojection loss --
+ *      utils/reprojection.py:81-96 (ps = 1), :99-127 (patch, ps odd) ----
+ * loss = sum_{b,k,i,j} m[b,i,j] * (Wu - Lu)^2 / (K * sum m),  K = C*ps*ps, with Lu/Ru the zero-padded
+ * ps x ps unfold of tgt/src and Wu = apply_disparity(Ru, sign*disp) (reprojection.py:102-118).
+ *   tgt, src : [B,C,H,W] (tgt = image compared against, src = image that is warped)
+ *   disp     : [B,1,H,W];  sign = -1 reproduces apply_disparity(src, -disp), +1 apply_disparity(src, disp)
+ *   mask     : [B,1,H,W] uint8 (0/1) or NULL (= all ones)
+ *   warped   : [B,C,H,W] or NULL; for ps == 1 the warped image (reprojection.py:89). (ps > 1: use az_patch_fold.)
+ *   gpre     : [B,1,H,W] or NULL; m * sum_k (Wu-Lu) * dWu/dxs, consumed by az_reproj_loss_bwd
+ *   loss_out : float[1];  stats: double[2] = {sum of squares, sum m} (device), kept for the backward
+ *   workspace: az_reproj_workspace_bytes(B,H) bytes, 16-byte aligned
+ * Empty mask => loss = NaN, as the reference (F.mse_loss of an empty selection). */
+int64_t az_reproj_workspace_bytes(int64_t B, int64_t H);
+int az_reproj_loss_fwd(const float* tgt, const float* src, const float* disp, float sign, const uint8_t* mask,
+                       const float* lin_x, const float* lin_y, int64_t ps,
+                       float* warped, float* gpre, float* loss_out, double* stats, void* workspace,
+                       int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
+/* gdisp[b,0,i,j] = gloss[0] * sign * 2/(K*sum m) * gpre[b,0,i,j] */
+int az_reproj_loss_bwd(const float* gpre, const double* stats, const float* gloss, float sign,
+                       float* gdisp, int64_t B, int64_t C, int64_t H, int64_t W, int64_t ps, void* stream);
+/* Visualisation output of get_reproj_error_patch: Fold (overlap-sum) of the warped unfolded planes,
+ * cropped by (ps-1)/2 (reprojection.py:120-125).  vis: [B,C,H,W]. */
+int az_patch_fold(const float* src, const float* disp, float sign, const float* lin_x, const float* lin_y,
+                  int64_t ps, float* vis, int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
+
+/* ---- a10: integer scatter warp -- utils/warp_ops.py:20-47 kernels + :55-95 host ----
+ * dst[n,c,y,j+disp[n,0,y,j]] = src[n,c,y,j]; among sources landing on one column the largest |disp| wins
+ * (== the reference kernels' last-writer order); holes = 0.  src,dst: [N,C,H,W] float32; disp: [N,1,H,W] int32.
+ * sign_flags: int32[1] device, zero-filled by the caller; bit0 set if any disp > 0, bit1 if any disp < 0
+ * (the reference asserts the disparities do not mix signs, warp_ops.py:73-77). May be NULL. */
+int az_scatter_warp(const float* src, const int32_t* disp, float* dst, int32_t* sign_flags,
+                    int64_t N, int64_t C, int64_t H, int64_t W, void* stream);
+
+/* ---- a11: temporal IR pattern -- tools/temporal_ir.py:35-40, 93-114 ----
+ * frames: [B,T,H,W] uint8 -> pattern [B,H,W] float32 in {0,1}: per-pixel least-squares slope over t,
+ * |fit[T-1]-fit[0]|/255, per-image min-max normalise, minus ks x ks box blur (BORDER_REFLECT_101),
+ * > threshold.  float64 arithmetic as numpy.  workspace: az_temporal_ir_workspace_bytes(B,H,W) bytes. */
+int64_t az_temporal_ir_workspace_bytes(int64_t B, int64_t H, int64_t W);
+int az_temporal_ir(const uint8_t* frames, float* pattern, void* workspace,
+                   int64_t B, int64_t T, int64_t H, int64_t W, int64_t ks, double threshold, void* stream);
+
+/* ---- a12: local contrast normalisation -- utils/reprojection.py:175-200 ----
+ * image: [B,Cin,H,W], only channel 0 is used (:184-185); zero-padded ks x ks window mean and population
+ * std; normed = (img - mean)/(std + eps).  normed, std: [B,1,H,W]. */
+int az_local_contrast_norm(const float* image, float* normed, float* std, int64_t B, int64_t Cin,
+                           int64_t H, int64_t W, int64_t ks, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZ_STEREO_H */
