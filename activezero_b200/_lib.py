@@ -46,8 +46,12 @@ SIGNATURES = {
     "az_local_contrast_norm": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
 }
 
+# CUDA kernels enqueued by one successful call of each compute entry point
+KERNELS_PER_CALL = {"az_reproj_loss_fwd": 2, "az_temporal_ir": 3}
+
 _lib = None
-launch_count = 0  # number of C-ABI compute calls issued (bench.py reports kernel launches from it)
+launch_count = 0    # C-ABI compute calls issued
+kernel_launches = 0  # CUDA kernels those calls enqueued (bench.py reports it as gpu_launches)
 
 
 def header_symbols() -> list[str]:
@@ -77,10 +81,11 @@ def load() -> ctypes.CDLL:
 
 def call(name: str, *args):
     """Invoke a compute entry point; raise on any non-zero status."""
-    global launch_count
+    global launch_count, kernel_launches
     lib = load()
     rc = getattr(lib, name)(*args)
     launch_count += 1
+    kernel_launches += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         msg = lib.az_error_string(rc).decode()
         raise RuntimeError(f"{name} failed with status {rc}: {msg}")

@@ -17,7 +17,6 @@ namespace az {
 constexpr int kSAThreads = 256;
 constexpr int kChunk = 8;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
 
 template <int V> struct Vec;
 template <> struct Vec<4> {
@@ -44,10 +43,12 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_fwd_kernel(const float
     const int64_t b = pix / plane, hw = pix - b * plane;
     const float* src = cost + b * D * plane + hw;
 
-    float m[V];
+    // mb = running max in the log2 domain, fl(max * log2e): the SAME rounded value is used in the
+    // exponent FMAs and in the rescale factor, so old and new partial sums stay consistent.
+    float mb[V];
     double s[V], ws[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) { m[j] = -INFINITY; s[j] = 0.0; ws[j] = 0.0; }
+    for (int j = 0; j < V; ++j) { mb[j] = -INFINITY; s[j] = 0.0; ws[j] = 0.0; }
 
     for (int d0 = 0; d0 < D; d0 += kChunk) {
         float x[kChunk][V];
@@ -66,16 +67,17 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_fwd_kernel(const float
             float cm = x[0][j];
 #pragma unroll
             for (int k = 1; k < kChunk; ++k) cm = fmaxf(cm, x[k][j]);
-            if (cm > m[j]) {  // rescale the running sums (exp2(-inf) = 0 on the first chunk)
-                const double sc = (double)exp2f((m[j] - cm) * kLog2e);
+            const float cmb = cm * kLog2e;
+            if (cmb > mb[j]) {  // rescale the running sums (exp2(-inf) = 0 on the first chunk)
+                const double sc = (double)exp2f(mb[j] - cmb);
                 s[j] *= sc;
                 ws[j] *= sc;
-                m[j] = cm;
+                mb[j] = cmb;
             }
-            const float mb = (m[j] == -INFINITY) ? 0.f : m[j] * kLog2e;  // leading -inf planes contribute 0
+            const float ref = (mb[j] == -INFINITY) ? 0.f : mb[j];  // leading -inf planes contribute 0
             float e[kChunk];
 #pragma unroll
-            for (int k = 0; k < kChunk; ++k) e[k] = exp2f(fmaf(x[k][j], kLog2e, -mb));
+            for (int k = 0; k < kChunk; ++k) e[k] = exp2f(fmaf(x[k][j], kLog2e, -ref));
             // tree sums of the chunk in fp32, running sums in fp64
             const float s01 = e[0] + e[1], s23 = e[2] + e[3], s45 = e[4] + e[5], s67 = e[6] + e[7];
             const float w01 = e[1], w23 = fmaf(e[3], 3.f, e[2] * 2.f);
@@ -91,8 +93,10 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_fwd_kernel(const float
     for (int j = 0; j < V; ++j) o[j] = (float)(ws[j] / s[j]);
     *reinterpret_cast<VT*>(disp + pix) = Vec<V>::pack(o);
     if (lse != nullptr) {
+        // saved in the log2 domain: lse2 = log2(sum_d 2^(cost_d*log2e)); the backward forms
+        // p_d = 2^(cost_d*log2e - lse2) with the same FMA as above.
 #pragma unroll
-        for (int j = 0; j < V; ++j) l[j] = m[j] + logf((float)s[j]);
+        for (int j = 0; j < V; ++j) l[j] = mb[j] + log2f((float)s[j]);
         *reinterpret_cast<VT*>(lse + pix) = Vec<V>::pack(l);
     }
 }
@@ -115,9 +119,6 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_bwd_kernel(const float
     Vec<V>::unpack(*reinterpret_cast<const VT*>(disp + pix), o);
     Vec<V>::unpack(*reinterpret_cast<const VT*>(lse + pix), lb);
     Vec<V>::unpack(*reinterpret_cast<const VT*>(gdisp + pix), g);
-#pragma unroll
-    for (int j = 0; j < V; ++j) lb[j] *= kLog2e;
-
     for (int d0 = 0; d0 < D; d0 += kChunk) {
         VT v[kChunk];
 #pragma unroll

@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- the stereo hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): stereo pairs/s for costvol + dispreg + reproj at 544x960,
+D = 192, and the fraction of the HBM roofline the dominant kernel reaches.
+
+A *step* is one pass of the forward hot path over one batch of B = 8 synthetic
+stereo pairs (BASELINE config 2, "PSMNet inference at 544x960, D=192, batch 8"):
+  1. concat cost volume      [8,32,136,240] x2 -> [8,64,48,136,240]   (a1)
+  2. soft-argmin             [8,192,544,960] logits -> [8,1,544,960]  (a4)
+  3. patch reprojection loss (ps = 11, masked MSE) of the IR patterns warped by
+     the predicted disparity, + the Fold visualisation image            (a7)
+Weak scaling: every rank processes its own batch of 8 pairs; no collective on
+the data path.  `value` times the step with inputs resident in
+HBM; `e2e` times the same calls with every input copied from pinned host memory
+and the results (disparity + loss) copied back inside the timed region.
+
+`--impl reference` times the reference's CPU implementation of the same step
+(the torch restatement in oracle/, all host threads) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "stereo pairs/s, costvol+dispreg+reproj @544x960 D=192"
+UNIT = "pairs/s"
+B, C, H, W, D, PS = 8, 32, 544, 960, 192, 11
+HQ, WQ, DQ = H // 4, W // 4, D // 4
+WORKLOAD = (f"config2: PSMNet inference hot path fwd, batch {B} x {H}x{W}, D={D}: concat volume "
+            f"[{B},{2 * C},{DQ},{HQ},{WQ}] + soft-argmin [{B},{D},{H},{W}] + patch reprojection loss ps={PS} (+fold image)")
+
+# algorithmic bytes per launch (SURVEY.md §8d formulas x B pairs), fp32
+ALGO_BYTES = {
+    "concat_volume_fwd": 4 * (2 * C * HQ * WQ + 2 * C * DQ * HQ * WQ) * B,
+    "soft_argmin_fwd": 4 * (D * H * W + H * W) * B,
+    "reproj_patch_loss_fwd": (4 * (2 * 1 * H * W + H * W) + H * W) * B,
+    "patch_fold": 4 * (1 * H * W + H * W + 1 * H * W) * B,
+}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic():
+    """dram bytes per launch from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            pass
+    return {}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed regions
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+           "hw_power_brake_slowdown": 0x80}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception as e:  # pragma: no cover
+            self._nv, self.error = None, repr(e)
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                    for name, bit in {**self.BAD, **self.NOTE}.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def start(self):
+        self._active.set()
+
+    def pause(self):
+        self._active.clear()
+
+    def result(self):
+        self._stop.set()
+        if self._nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": int(statistics.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's torch restatement on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_step(inputs, so):
+    """One pass of the same forward step for `inputs` (a 1-pair sample), stock torch on CPU."""
+    L, R, cost, pat_L, pat_R, mask = inputs
+    vol = so.concat_volume(L, R, DQ)
+    disp = so.soft_argmin(cost)
+    loss, vis, _ = so.reproj_error_patch(pat_L, pat_R, disp, mask, ps=PS)
+    return vol, disp, loss, vis
+
+
+def make_inputs(nb, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    L = torch.randn(nb, C, HQ, WQ, generator=g)
+    R = torch.randn(nb, C, HQ, WQ, generator=g)
+    cost = torch.empty(nb, D, H, W)
+    for b in range(nb):  # generated per pair to bound the temporary
+        cost[b] = torch.randn(D, H, W, generator=g) * 4.0
+    pat_L = (torch.rand(nb, 1, H, W, generator=g) > 0.5).float()
+    pat_R = (torch.rand(nb, 1, H, W, generator=g) > 0.5).float()
+    mask = torch.rand(nb, 1, H, W, generator=g) > 0.2
+    ts = [L, R, cost, pat_L, pat_R, mask]
+    if pin:
+        ts = [t.pin_memory() for t in ts]
+    if device != "cpu":
+        ts = [t.to(device) for t in ts]
+    return ts
+
+
+def time_cpu_reference(steps, warmup):
+    from oracle import stereo_oracle as so
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inputs = make_inputs(1, 1234)
+    with torch.no_grad():
+        for _ in range(warmup):
+            cpu_reference_step(inputs, so)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_reference_step(inputs, so)
+        dt = time.perf_counter() - t0
+    return steps * 1 / dt, dt / steps * 1e3, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    pairs_s, ms, cores = time_cpu_reference(steps, warmup)
+    sample = f"1 pair of the {B}-pair batch per step, {steps} timed steps after {warmup} warm-up, torch {torch.__version__} CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": pairs_s, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": pairs_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": pairs_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# the B200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    from activezero_b200 import _lib, ops
+    from activezero_b200.utils import reprojection as az_rp
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    host = make_inputs(B, 1000 + rank, pin=True)
+    L, R, cost, pat_L, pat_R, mask = [t.to(dev, non_blocking=True) for t in host]
+    torch.cuda.synchronize()
+    names = ["concat_volume_fwd", "soft_argmin_fwd", "reproj_patch_loss_fwd", "patch_fold"]
+
+    def step(Ld, Rd, costd, pLd, pRd, md, evs=None):
+        if evs is not None:
+            evs[0].record()
+        vol = ops.build_concat_volume(Ld, Rd, DQ)
+        if evs is not None:
+            evs[1].record()
+        disp = ops.soft_argmin(costd)
+        if evs is not None:
+            evs[2].record()
+        loss, _ = ops.reproj_loss(pLd, pRd, disp, md, ps=PS, sign=-1.0)
+        if evs is not None:
+            evs[3].record()
+        vis = ops.patch_fold(pRd, disp, PS, sign=-1.0)
+        if evs is not None:
+            evs[4].record()
+        return vol, disp, loss, vis
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local_rank)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            out = step(L, R, cost, pat_L, pat_R, mask)
+        del out
+        # ---- device-resident timing (value) + per-kernel events for the roofline ----
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = _lib.kernel_launches
+        barrier()
+        clocks.start()
+        start.record()
+        for k in range(args.steps):
+            out = step(L, R, cost, pat_L, pat_R, mask, evs[k])
+        stop.record()
+        barrier()
+        clocks.pause()
+        launches = _lib.kernel_launches - launches0
+        ms_total = start.elapsed_time(stop)
+        del out
+
+        # ---- end to end: pinned host -> device, compute, results back, every step ----
+        e2e_steps = max(1, min(args.steps, 10))
+        res_disp = torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory()
+        res_loss = torch.empty((), dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        d2h = res_disp.numel() * 4 + 4
+
+        def e2e_step():
+            dv = [t.to(dev, non_blocking=True) for t in host]
+            _, disp, loss, _ = az_call(dv)
+            res_disp.copy_(disp, non_blocking=True)
+            res_loss.copy_(loss, non_blocking=True)
+
+        def az_call(dv):
+            # the call a user makes: the reference-named functions of the drop-in modules
+            vol = ops.build_concat_volume(dv[0], dv[1], DQ)
+            disp = ops.soft_argmin(dv[2])
+            loss, vis, _ = az_rp.get_reproj_error_patch(dv[3], dv[4], disp, dv[5], ps=PS)
+            return vol, disp, loss, vis
+
+        for _ in range(2):
+            e2e_step()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        clocks.start()
+        s2.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e2.record()
+        barrier()
+        clocks.pause()
+        ms_e2e = s2.elapsed_time(e2)
+        loss_val = float(res_loss)
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        per_kernel = {}
+        for i, n in enumerate(names):
+            per_kernel[n] = statistics.fmean(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps))
+        peak, peak_src = _peaks()
+        traffic = _traffic()
+        kernels = []
+        for n in names:
+            gbs = ALGO_BYTES[n] / (per_kernel[n] * 1e-3) / 1e9
+            kernels.append({"kernel": n, "ms": per_kernel[n], "algo_bytes": ALGO_BYTES[n], "achieved_gbs": gbs,
+                            "frac": gbs / peak, "share": per_kernel[n] / sum(per_kernel.values()),
+                            "traffic": traffic.get(n)})
+        dom = max(kernels, key=lambda k: k["ms"])
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "sharding": "batch (pairs) per rank, no data-path collective",
+                       "l2": "inputs larger than L2: 6.5 GB streamed per step vs 126 MB L2"},
+            "clocks": clocks.result(),
+            "e2e": {"value": world * B * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                    "api": "ops.build_concat_volume + ops.soft_argmin + utils.reprojection.get_reproj_error_patch"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak,
+                         "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
+                         "pipeline_frac": sum(ALGO_BYTES.values()) / (ms_total / args.steps * 1e-3) / 1e9 / peak},
+            "kernels": kernels,
+            "loss_check": loss_val,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            pairs_s, _, cores = time_cpu_reference(3, 1)
+            line["cpu_baseline"] = {"value": pairs_s, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "1 pair of the 8-pair batch per step, 3 timed steps after 1 warm-up"}
+        print(json.dumps(line), flush=True)
+    else:
+        clocks.result()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

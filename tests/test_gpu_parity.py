@@ -189,15 +189,22 @@ def test_soft_argmin_edge_values():
 
 
 def test_soft_argmin_full_size():
-    """BASELINE config 2 head (B=2 of 8): [2,192,544,960] logits."""
+    """BASELINE config 2 head (B=2 of 8): [2,192,544,960] logits.  Over 10^6 pixels the fp32
+    reference's own rounding noise reaches ~1e-4 px at the tail, so the kernel is held to 2e-5 px
+    against the exact (fp64) value -- 5x inside the gate -- and its distance to the fp32
+    reference (stock torch on the GPU as the checker) must be explained by that reference's
+    distance to exact."""
     torch.manual_seed(6)
     cost = torch.randn(2, 192, 544, 960, device=DEV) * 4.0
     out = ops.soft_argmin(cost)
-    ref32 = so.soft_argmin(cost)  # stock torch on the GPU as the checker
-    assert float((out - ref32).abs().max()) <= 1e-4
-    ref64 = _sa_ref64(cost[:1])
-    assert float((out[:1].double() - ref64).abs().max()) <= 2e-5
-    # shift invariance (softmax property), exact for an exactly representable shift
+    ref32 = so.soft_argmin(cost)
+    ref64 = torch.cat([_sa_ref64(cost[b:b + 1]) for b in range(2)])
+    mine = float((out.double() - ref64).abs().max())
+    theirs = float((ref32.double() - ref64).abs().max())
+    assert mine <= 2e-5, mine
+    assert float((out - ref32).abs().max()) <= theirs + 2e-5
+    assert float(((out - ref32).abs() <= 1e-4).float().mean()) >= 0.99
+    # shift invariance (softmax property)
     out_shift = ops.soft_argmin(cost + 8.0)
     assert float((out_shift - out).abs().max()) <= 1e-4
     assert float(out.min()) >= 0.0 and float(out.max()) <= 191.0
@@ -335,8 +342,8 @@ def test_reproj_patch_empty_mask_nan_and_flags(golden):
 
 
 def test_reproj_full_size_properties():
-    """544x960 (config 2 frame).  Stock torch on the GPU runs the restatement as
-    the checker for one pair; exact properties cover the batch: the loss scales by
+    """544x960 (config 2 frame).  The CPU oracle checks one full-size pair;
+    exact properties cover the batch: the loss scales by
     a^2 when both images scale by a = 2, and the disparity gradient is supported
     on the mask only."""
     torch.manual_seed(12)
@@ -352,20 +359,16 @@ def test_reproj_full_size_properties():
     loss, vis, _ = az_rp.get_reproj_error_patch(L, R, dg, mask, ps=11)
     loss.backward()
     assert float(dg.grad[~mask].abs().max()) == 0.0 and float(dg.grad[mask].abs().max()) > 0.0
-    dr = d[:1].clone().requires_grad_(True)
-    rl, rvis, _ = so.reproj_error_patch(L[:1], R[:1], dr, mask[:1], ps=11)  # torch on GPU, 3 x 253 MB intermediates
+    # one full-size pair against the CPU oracle (same fp32 sample positions bit for bit)
+    dr = d[:1].cpu().clone().requires_grad_(True)
+    rl, rvis, _ = so.reproj_error_patch(L[:1].cpu(), R[:1].cpu(), dr, mask[:1].cpu(), ps=11)
     rl.backward()
-    l0, v0, _ = az_rp.get_reproj_error_patch(L[:1], R[:1], d[:1], mask[:1], ps=11)
-    np.testing.assert_allclose(l0.item(), rl.item(), rtol=1e-5)
-    close(v0, rvis, rtol=1e-4, floor=1e-5)
     d0 = d[:1].clone().requires_grad_(True)
-    az_rp.get_reproj_error_patch(L[:1], R[:1], d0, mask[:1], ps=11)[0].backward()
-    # torch's CUDA grid_sampler rounds the sample position differently from its CPU kernel (which
-    # the kernels follow bit for bit), so a few pixels sit on the other side of an integer
-    # boundary where d(loss)/d(disp) jumps: require 99.9 % element-wise agreement.
-    err = (d0.grad - dr.grad).abs()
-    tol = 1e-5 * float(dr.grad.abs().max()) + 1e-4 * dr.grad.abs()
-    assert float((err <= tol).float().mean()) > 0.999
+    l0, v0, _ = az_rp.get_reproj_error_patch(L[:1], R[:1], d0, mask[:1], ps=11)
+    l0.backward()
+    np.testing.assert_allclose(l0.item(), rl.item(), rtol=1e-5)
+    close(v0, rvis)
+    close(d0.grad, dr.grad)
 
 
 def test_reproj_diff_ratio_golden(golden):
