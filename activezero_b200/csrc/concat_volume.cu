@@ -8,11 +8,13 @@
 // sweeps the Dq disparity planes with coalesced, streaming 128-bit stores.  Each right-feature
 // row is read from HBM exactly once per sweep.
 //
-// Backward is a pure load stream.  The gradient slab of one (b, channel, row-tile) -- Dq
-// contiguous runs of rows -- is pulled into shared memory with 1-D bulk async copies (TMA
-// engine, mbarrier completion), all issued up front, and reduced along the disparity axis
-// (left half: straight down; right half: along the x+i diagonal) by one thread per output
-// column, in a fixed order: gather-style and atomic-free.
+// Backward is a pure load stream: one thread per float4 of gL / gR walks the Dq disparity planes
+// with 8 independent 128-bit streaming loads in flight (left half: straight down; right half:
+// along the x+i diagonal, read as two aligned float4 per plane and a static register window),
+// accumulating in a fixed order: gather-style and atomic-free.  The zero triangle x < i of the
+// gradient volume is never read.  (A first version staged the slab in shared memory with 1-D
+// bulk async copies and reached only 47 % of the measured HBM peak against 97 % for this
+// direct-load form; see profiles/README.md.)
 #include "common.cuh"
 
 namespace az {
@@ -134,94 +136,74 @@ __global__ void __launch_bounds__(256) concat_fwd_scalar_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------------------------
-// backward, bulk-async-copy path (W % 4 == 0, aligned): grid = (ceil(H/ny), 2C, B)
-// smem: [chunk][ny*W] floats of gradient slab + mbarriers.
+// backward, direct path (W % 4 == 0, aligned): one thread per float4 of gL / gR, serial loop over
+// the disparity planes with 8 independent 128-bit streaming loads in flight.  Coalesced along W;
+// the zero triangle x < i of the volume gradient is never read.  grid = (ceil(H*W/4/256), 2C, B)
+// Right half: output columns x..x+3 need g[i][x+i .. x+i+3]; with i = 4m+r that is the window
+// [r, r+4) of the two ALIGNED float4 at columns x+4m and x+4m+4, selected with static register
+// indices inside the unrolled r loop.
 // ------------------------------------------------------------------------------------------
-constexpr int kBwdThreads = 256;
-constexpr int kBwdGroup = 8;  // disparity planes per mbarrier
+__device__ __forceinline__ float sel7(const float4& a, const float4& b, int k) {
+    switch (k) {
+        case 0: return a.x; case 1: return a.y; case 2: return a.z; case 3: return a.w;
+        case 4: return b.x; case 5: return b.y; default: return b.z;
+    }
+}
 
-__global__ void __launch_bounds__(kBwdThreads) concat_bwd_bulk_kernel(const float* __restrict__ gvol,
-                                                                     float* __restrict__ gL,
-                                                                     float* __restrict__ gR, int C, int H,
-                                                                     int W, int Dq, int ny, int chunk) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(256) concat_bwd_direct_kernel(const float* __restrict__ gvol,
+                                                                float* __restrict__ gL, float* __restrict__ gR,
+                                                                int C, int H, int W, int Dq) {
+    const int W4 = W >> 2;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= H * W4) return;
     const int oc = blockIdx.y, b = blockIdx.z;
     const bool right = oc >= C;
     float* gout = right ? gR : gL;
     if (gout == nullptr) return;
     const int c = right ? oc - C : oc;
-    const int y0 = blockIdx.x * ny;
-    const int rows = min(ny, H - y0);
-    const int n = rows * W;                     // floats per disparity plane of this tile
-    const int slab = ny * W;                    // smem stride per plane
-    const int ngroups_cap = (chunk + kBwdGroup - 1) / kBwdGroup;
-    float* s = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)chunk * slab * sizeof(float));
+    const int y = p / W4, x = (p - y * W4) * 4;
     const size_t HW = (size_t)H * W;
-    const float* gsrc = gvol + ((size_t)b * 2 * C + oc) * Dq * HW + (size_t)y0 * W;
-
-    if (threadIdx.x == 0) {
-        for (int g = 0; g < ngroups_cap; ++g) mbar_init(&bars[g], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    constexpr int kOut = 4;  // outputs per thread (n <= kOut * kBwdThreads is guaranteed by the host)
-    float acc[kOut];
-    int ox[kOut];
+    const float* g = gvol + ((size_t)b * 2 * C + oc) * Dq * HW + (size_t)p * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!right) {
+        const int lim = min(Dq, x + 4);  // planes i > x+3 only hold the zero triangle for these columns
+        for (int i0 = 0; i0 < lim; i0 += 8) {
+            float4 v[8];
 #pragma unroll
-    for (int k = 0; k < kOut; ++k) {
-        acc[k] = 0.f;
-        const int t = threadIdx.x + k * kBwdThreads;
-        ox[k] = t < n ? t % W : -1;
-    }
-
-    uint32_t parity = 0;
-    for (int i0 = 0; i0 < Dq; i0 += chunk) {
-        const int cnt = min(chunk, Dq - i0);
-        const int ngroups = (cnt + kBwdGroup - 1) / kBwdGroup;
-        if (threadIdx.x == 0) {
-            // generic-proxy reads of the previous chunk are ordered before these async writes
-            // by the __syncthreads at the end of the loop body + this proxy fence.
-            fence_proxy_async();
-            for (int g = 0; g < ngroups; ++g) {
-                const int gi0 = g * kBwdGroup, gcnt = min(kBwdGroup, cnt - gi0);
-                mbar_arrive_expect_tx(&bars[g], (uint32_t)(gcnt * n * sizeof(float)));
-                for (int i = gi0; i < gi0 + gcnt; ++i)
-                    bulk_g2s(s + (size_t)i * slab, gsrc + (size_t)(i0 + i) * HW, (uint32_t)(n * sizeof(float)),
-                             &bars[g]);
+            for (int k = 0; k < 8; ++k)
+                v[k] = (i0 + k < lim) ? ld_stream(reinterpret_cast<const float4*>(g + (size_t)(i0 + k) * HW)) : zero;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = i0 + k;
+                acc.x += (x + 0 >= i) ? v[k].x : 0.f;
+                acc.y += (x + 1 >= i) ? v[k].y : 0.f;
+                acc.z += (x + 2 >= i) ? v[k].z : 0.f;
+                acc.w += v[k].w;  // x+3 >= i holds for every loaded plane
             }
         }
-        for (int g = 0; g < ngroups; ++g) {
-            mbar_wait(&bars[g], parity);
-            const int gi0 = g * kBwdGroup, gcnt = min(kBwdGroup, cnt - gi0);
+    } else {
+        const int lim = min(Dq, W - x);  // x+i < W
+        for (int m4 = 0; m4 < lim; m4 += 4) {
+            float4 A[4], Bv[4];
+            const bool inB = (x + m4 + 4) < W;
 #pragma unroll
-            for (int k = 0; k < kOut; ++k) {
-                if (ox[k] < 0) continue;
-                const int t = threadIdx.x + k * kBwdThreads;
-                const float* sp = s + (size_t)gi0 * slab + t;
-                if (right) {
-                    // gR[x] += g[i][x+i]  while x+i < W
-                    for (int i = 0; i < gcnt; ++i) {
-                        const int ii = i0 + gi0 + i;
-                        if (ox[k] + ii < W) acc[k] += sp[(size_t)i * slab + ii];
-                    }
-                } else {
-                    // gL[x] += g[i][x]  while i <= x
-                    for (int i = 0; i < gcnt; ++i) {
-                        const int ii = i0 + gi0 + i;
-                        if (ii <= ox[k]) acc[k] += sp[(size_t)i * slab];
-                    }
-                }
+            for (int r = 0; r < 4; ++r) {
+                const bool on = (m4 + r) < lim;
+                const float* q = g + (size_t)(m4 + r) * HW + m4;
+                A[r] = on ? __ldg(reinterpret_cast<const float4*>(q)) : zero;
+                Bv[r] = (on && inB) ? __ldg(reinterpret_cast<const float4*>(q + 4)) : zero;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                acc.x += sel7(A[r], Bv[r], r + 0);
+                acc.y += sel7(A[r], Bv[r], r + 1);
+                acc.z += sel7(A[r], Bv[r], r + 2);
+                acc.w += sel7(A[r], Bv[r], r + 3);
             }
         }
-        parity ^= 1;
-        __syncthreads();
     }
-    float* o = gout + ((size_t)b * C + c) * HW + (size_t)y0 * W;
-#pragma unroll
-    for (int k = 0; k < kOut; ++k)
-        if (ox[k] >= 0) o[threadIdx.x + k * kBwdThreads] = acc[k];
+    *reinterpret_cast<float4*>(gout + ((size_t)b * C + c) * HW + (size_t)p * 4) = acc;
 }
 
 // backward, scalar fallback: one thread per output element.  grid = (ceil(H*W/256), 2C, B)
@@ -293,37 +275,12 @@ extern "C" int az_concat_volume_bwd(const float* gvol, float* gL, float* gR, int
     if (H * W >= (1ll << 31) / 4 || B > 65535 || 2 * C > 65535) return AZ_ERR_BAD_ARG;
     if (!gL && !gR) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec = (W % 4 == 0) && aligned16(gvol) && W <= 4 * kBwdThreads;
-    if (vec) {
-        // rows per tile: as many as 4*256 outputs allow, capped so a full-Dq slab fits ~96 KB
-        // (two CTAs per SM) when possible.
-        int ny = (int)((4 * kBwdThreads) / W);
-        if (ny > H) ny = (int)H;
-        const size_t budget = 96 * 1024;
-        while (ny > 1 && (size_t)ny * W * 4 * Dq > budget) --ny;
-        const size_t slab_bytes = (size_t)ny * W * sizeof(float);
-        int chunk = (int)Dq;
-        const size_t hard = 200 * 1024;
-        if (slab_bytes * chunk > budget) {
-            chunk = (int)(budget / slab_bytes);
-            if (chunk < kBwdGroup) chunk = (int)((hard / slab_bytes) < (size_t)Dq ? (hard / slab_bytes) : Dq);
-        }
-        if (chunk >= 1) {
-            const int ngroups = (chunk + kBwdGroup - 1) / kBwdGroup;
-            const size_t smem = slab_bytes * chunk + (size_t)ngroups * sizeof(uint64_t);
-            static bool attr_done = false;
-            if (!attr_done) {
-                cudaError_t e = cudaFuncSetAttribute(concat_bwd_bulk_kernel,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-                if (e != cudaSuccess) return (int)e;
-                attr_done = true;
-            }
-            dim3 grid((unsigned)ceil_div(H, ny), (unsigned)(2 * C), (unsigned)B);
-            concat_bwd_bulk_kernel<<<grid, kBwdThreads, smem, st>>>(gvol, gL, gR, (int)C, (int)H, (int)W, (int)Dq, ny,
-                                                                   chunk);
-            AZ_LAUNCH_CHECK();
-            return 0;
-        }
+    const bool vec4 = (W % 4 == 0) && aligned16(gvol) && (!gL || aligned16(gL)) && (!gR || aligned16(gR));
+    if (vec4) {
+        dim3 grid((unsigned)ceil_div(H * (W / 4), 256), (unsigned)(2 * C), (unsigned)B);
+        concat_bwd_direct_kernel<<<grid, 256, 0, st>>>(gvol, gL, gR, (int)C, (int)H, (int)W, (int)Dq);
+        AZ_LAUNCH_CHECK();
+        return 0;
     }
     dim3 grid((unsigned)ceil_div(H * W, 256), (unsigned)(2 * C), (unsigned)B);
     concat_bwd_scalar_kernel<<<grid, 256, 0, st>>>(gvol, gL, gR, (int)C, (int)H, (int)W, (int)Dq);

@@ -230,15 +230,126 @@ __global__ void __launch_bounds__(256) reproj_bwd_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------
 // Fold (overlap-sum) of the warped unfolded planes, cropped: reprojection.py:120-125.
 // vis[b,c,y,x] = sum_{ky,kx} Wu[(c,ky,kx)][y+p-ky, x+p-kx].   grid = (H, C, B)
-// smem: Bk[ps][Wp] blended source rows | XS[ps][W] sample x of source row i = y+p-ky
+//
+// Source-centric + systolic: for tap row ky the contributing source row is i = y+p-ky.  A lane
+// owns two adjacent SOURCE pixels j of that row, computes their sampling parameters once and
+// walks the ps horizontal taps with a sliding window over the blended source row
+// (Wu[kx] = bx0*A[kx] + bx1*A[kx+1]); tap kx of source j lands on output x = j+kx-p, so the
+// sum over kx is a diagonal across lanes, accumulated with a shuffle chain
+//     acc_s <- Wu_s[k] + acc_{s+1}         (s = source index, one __shfl_down per two taps).
+// After ps steps the lane of source s holds the output x = s+p; a pass of one warp covers 64
+// sources and yields 64-(ps-1) outputs.  Per tap: 1 LDS + 2 FMA + 1 FADD + 1/2 SHFL.
+// smem: Bk[ps][Wp] blended source rows (Wp = W + 2*(p+1), data starts at column OFF = p+1).
 // ------------------------------------------------------------------------------------------
-constexpr int kFoldThreads = 512;
+constexpr int kFoldThreads = 256;
 
-__global__ void __launch_bounds__(kFoldThreads) patch_fold_kernel(const float* __restrict__ src,
+struct FoldSrc {
+    int base;        // index of A[0] in the blended row
+    float bx0, bx1;  // corner weights with validity folded in
+};
+
+__device__ __forceinline__ FoldSrc fold_src(const float* __restrict__ drow, const float* __restrict__ lin_x, float sign,
+                                            int j, int W, int OFF, int p) {
+    FoldSrc f;
+    f.base = OFF;  // any in-range index; weights are 0
+    f.bx0 = 0.f;
+    f.bx1 = 0.f;
+    if (j >= 0 && j < W) {
+        const Axis ax = make_axis(sample_pos(__ldg(lin_x + j), __fdiv_rn(sign * __ldg(drow + j), (float)W), (float)W), W);
+        f.base = OFF + min(max(ax.i0, -1), W - 1) - p;
+        f.bx0 = ax.v0 ? ax.e : 0.f;
+        f.bx1 = ax.v1 ? ax.w : 0.f;
+    }
+    return f;
+}
+
+template <int PS>
+__global__ void __launch_bounds__(kFoldThreads) patch_fold_systolic_kernel(const float* __restrict__ src,
+                                                                          const float* __restrict__ disp, float sign,
+                                                                          const float* __restrict__ lin_x,
+                                                                          const float* __restrict__ lin_y,
+                                                                          float* __restrict__ vis, int C, int H, int W) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int p = (PS - 1) / 2, OFF = p + 1;
+    constexpr int STEP = 64 - (PS - 1);  // outputs per warp pass
+    const int y = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
+    const int Wp = W + 2 * OFF;
+    const size_t HW = (size_t)H * W;
+    const float* sp = src + ((size_t)b * C + c) * HW;
+    const float* dp = disp + (size_t)b * HW;
+
+    // blended source rows, one per tap row
+    for (int ky = 0; ky < PS; ++ky) {
+        const int i = y + p - ky;
+        const bool rowok = (i >= 0) && (i < H);
+        float ay0 = 0.f, ay1 = 0.f;
+        int r0 = 0;
+        if (rowok) {
+            const Axis ay = make_axis(sample_pos(__ldg(lin_y + i), 0.0f, (float)H), H);
+            ay0 = ay.v0 ? ay.e : 0.f;
+            ay1 = ay.v1 ? ay.w : 0.f;
+            r0 = ay.i0 + ky - p;  // image row read by corner y0 of tap row ky
+        }
+        for (int xx = threadIdx.x; xx < Wp; xx += kFoldThreads) {
+            const int x = xx - OFF;
+            float v = 0.f;
+            if (rowok && x >= 0 && x < W) {
+                const float a = (r0 >= 0 && r0 < H) ? __ldg(sp + (size_t)r0 * W + x) : 0.f;
+                const float bb = (r0 + 1 >= 0 && r0 + 1 < H) ? __ldg(sp + (size_t)(r0 + 1) * W + x) : 0.f;
+                v = fmaf(ay1, bb, ay0 * a);
+            }
+            sm[ky * Wp + xx] = v;
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kFoldThreads >> 5;
+    const int npass = (W + STEP - 1) / STEP;
+    float* orow = vis + ((size_t)b * C + c) * HW + (size_t)y * W;
+    for (int q = warp; q < npass; q += nwarps) {
+        const int x_out = q * STEP + 2 * lane;  // output column of this lane's first source
+        const int j0 = x_out - p;               // its two sources
+        float tot0 = 0.f, tot1 = 0.f;
+#pragma unroll 1
+        for (int ky = 0; ky < PS; ++ky) {
+            const int i = y + p - ky;
+            if (i < 0 || i >= H) continue;  // warp-uniform
+            const float* drow = dp + (size_t)i * W;
+            const FoldSrc s0 = fold_src(drow, lin_x, sign, j0, W, OFF, p);
+            const FoldSrc s1 = fold_src(drow, lin_x, sign, j0 + 1, W, OFF, p);
+            const float* r0 = sm + ky * Wp + s0.base;
+            const float* r1 = sm + ky * Wp + s1.base;
+            float a0 = r0[0], a1 = r1[0];
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < PS; ++k) {
+                const float n0 = r0[k + 1], n1 = r1[k + 1];
+                const float w0 = fmaf(s0.bx1, n0, s0.bx0 * a0);
+                const float w1 = fmaf(s1.bx1, n1, s1.bx0 * a1);
+                const float from_next = __shfl_down_sync(0xffffffffu, acc0, 1);
+                acc0 = w0 + acc1;
+                acc1 = w1 + from_next;
+                a0 = n0;
+                a1 = n1;
+            }
+            tot0 += acc0;
+            tot1 += acc1;
+        }
+        if (2 * lane < STEP) {
+            if (x_out < W) orow[x_out] = tot0;
+            if (x_out + 1 < W) orow[x_out + 1] = tot1;
+        }
+    }
+}
+
+// generic fallback (any odd ps): output-centric gather.  grid = (H, C, B)
+// smem: Bk[ps][Wp] blended source rows | XS[ps][W] sample x of source row i = y+p-ky
+__global__ void __launch_bounds__(512) patch_fold_kernel(const float* __restrict__ src,
                                                                  const float* __restrict__ disp, float sign,
                                                                  const float* __restrict__ lin_x,
                                                                  const float* __restrict__ lin_y, int ps,
                                                                  float* __restrict__ vis, int C, int H, int W) {
+    constexpr int kT = 512;
     extern __shared__ __align__(16) float sm[];
     const int y = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
     const int p = (ps - 1) >> 1, OFF = p + 1, Wp = W + 2 * OFF;
@@ -259,7 +370,7 @@ __global__ void __launch_bounds__(kFoldThreads) patch_fold_kernel(const float* _
             ay1 = ay.v1 ? ay.w : 0.f;
             r0 = ay.i0 + ky - p;  // image row read by corner y0 of tap row ky
         }
-        for (int xx = threadIdx.x; xx < Wp; xx += kFoldThreads) {
+        for (int xx = threadIdx.x; xx < Wp; xx += kT) {
             const int x = xx - OFF;
             float v = 0.f;
             if (rowok && x >= 0 && x < W) {
@@ -269,14 +380,14 @@ __global__ void __launch_bounds__(kFoldThreads) patch_fold_kernel(const float* _
             }
             Bk[ky * Wp + xx] = v;
         }
-        for (int j = threadIdx.x; j < W; j += kFoldThreads) {
+        for (int j = threadIdx.x; j < W; j += kT) {
             float xs = -8.0f;  // floor = -8: both corners invalid
             if (rowok) xs = sample_pos(__ldg(lin_x + j), __fdiv_rn(sign * dp[(size_t)i * W + j], (float)W), (float)W);
             XS[ky * W + j] = xs;
         }
     }
     __syncthreads();
-    for (int x = threadIdx.x; x < W; x += kFoldThreads) {
+    for (int x = threadIdx.x; x < W; x += kT) {
         float a0 = 0.f, a1 = 0.f;
         for (int ky = 0; ky < ps; ++ky) {
             const float* bk = Bk + ky * Wp + OFF;
@@ -385,11 +496,36 @@ extern "C" int az_reproj_loss_bwd(const float* gpre, const double* stats, const 
     return 0;
 }
 
+template <int PS>
+static int launch_fold(const float* src, const float* disp, float sign, const float* lin_x, const float* lin_y, float* vis,
+                       int B, int C, int H, int W, cudaStream_t st) {
+    const size_t Wp = (size_t)W + 2 * ((PS - 1) / 2 + 1);
+    const size_t smem = (size_t)PS * Wp * sizeof(float);
+    if (smem > 220 * 1024) return AZ_ERR_BAD_ARG;
+    cudaError_t e = cudaFuncSetAttribute(patch_fold_systolic_kernel<PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(220 * 1024));
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)H, (unsigned)C, (unsigned)B);
+    patch_fold_systolic_kernel<PS><<<grid, kFoldThreads, smem, st>>>(src, disp, sign, lin_x, lin_y, vis, C, H, W);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int az_patch_fold(const float* src, const float* disp, float sign, const float* lin_x, const float* lin_y,
                              int64_t ps, float* vis, int64_t B, int64_t C, int64_t H, int64_t W, void* stream) {
     if (!src || !disp || !lin_x || !lin_y || !vis || B <= 0 || C <= 0 || H <= 0 || W <= 0 || ps < 1 || (ps % 2) == 0)
         return AZ_ERR_BAD_ARG;
     if (B > 65535 || C > 65535 || H * W >= (1ll << 31)) return AZ_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ps) {
+        case 1: return launch_fold<1>(src, disp, sign, lin_x, lin_y, vis, (int)B, (int)C, (int)H, (int)W, st);
+        case 3: return launch_fold<3>(src, disp, sign, lin_x, lin_y, vis, (int)B, (int)C, (int)H, (int)W, st);
+        case 5: return launch_fold<5>(src, disp, sign, lin_x, lin_y, vis, (int)B, (int)C, (int)H, (int)W, st);
+        case 7: return launch_fold<7>(src, disp, sign, lin_x, lin_y, vis, (int)B, (int)C, (int)H, (int)W, st);
+        case 9: return launch_fold<9>(src, disp, sign, lin_x, lin_y, vis, (int)B, (int)C, (int)H, (int)W, st);
+        case 11: return launch_fold<11>(src, disp, sign, lin_x, lin_y, vis, (int)B, (int)C, (int)H, (int)W, st);
+        case 13: return launch_fold<13>(src, disp, sign, lin_x, lin_y, vis, (int)B, (int)C, (int)H, (int)W, st);
+        default: break;
+    }
     const int p = (int)(ps - 1) / 2;
     const size_t Wp = (size_t)W + 2 * (p + 1);
     const size_t smem = (size_t)ps * (Wp + W) * sizeof(float);
@@ -398,8 +534,7 @@ extern "C" int az_patch_fold(const float* src, const float* disp, float sign, co
                                          (int)(220 * 1024));
     if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)H, (unsigned)C, (unsigned)B);
-    patch_fold_kernel<<<grid, kFoldThreads, smem, (cudaStream_t)stream>>>(src, disp, sign, lin_x, lin_y, (int)ps, vis,
-                                                                         (int)C, (int)H, (int)W);
+    patch_fold_kernel<<<grid, 512, smem, st>>>(src, disp, sign, lin_x, lin_y, (int)ps, vis, (int)C, (int)H, (int)W);
     AZ_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""Per-kernel sweep of the hot path on one B200 (BASELINE config 5): every forward
+and backward kernel at D in {96,192,288} x (H/4,W/4) in {64x128, 136x240, 272x480},
+achieved GB/s on the ALGORITHMIC bytes against the measured HBM peak.
+
+    python benchmarks/kernel_sweep.py [--quick] [--out profiles/rN_kernel_sweep.json]
+
+Timing: CUDA events on the launch stream, 3 warm-ups, >= 10 timed launches; batch
+chosen so that every launch streams >= ~1.5 GB (>> 126 MB L2) where the op is
+volume-sized, and a 256 MB L2 flush write between launches for the image-sized ops.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from activezero_b200 import _lib, ops  # noqa: E402
+
+DEV = "cuda:0"
+C, G, PS = 32, 8, 11
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+_flush = None
+
+
+def time_ms(fn, iters=10, warm=3, flush=False):
+    global _flush
+    if flush and _flush is None:
+        _flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)
+    for _ in range(warm):
+        fn()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    torch.cuda.synchronize()
+    for a, b in evs:
+        if flush:
+            _flush.fill_(1)
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2]
+
+
+def sweep(quick):
+    pk = peak()
+    rows = []
+
+    def add(kernel, cfg, ms, nbytes):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        rows.append({"kernel": kernel, **cfg, "ms": round(ms, 4), "algo_MB": round(nbytes / 1e6, 2),
+                     "GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / pk, 3)})
+        print(json.dumps(rows[-1]), flush=True)
+
+    sizes = [(64, 128), (136, 240), (272, 480)]
+    disps = [96, 192, 288]
+    if quick:
+        sizes, disps = [(136, 240)], [192]
+    for (Hq, Wq) in sizes:
+        for D in disps:
+            Dq, H, W = D // 4, 4 * Hq, 4 * Wq
+            vol_bytes = 4 * 2 * C * Dq * Hq * Wq
+            B = max(1, min(8, int(1.6e9 // vol_bytes)))
+            cfg = {"Hq": Hq, "Wq": Wq, "D": D, "B": B, "int64_index": B * 2 * C * Dq * Hq * Wq >= 2 ** 31}
+            torch.manual_seed(0)
+            L = torch.randn(B, C, Hq, Wq, device=DEV)
+            R = torch.randn(B, C, Hq, Wq, device=DEV)
+            feat_b = 4 * B * C * Hq * Wq
+            # concat
+            vol = ops.build_concat_volume(L, R, Dq)
+            add("concat_volume_fwd", cfg, time_ms(lambda: ops.build_concat_volume(L, R, Dq)), 2 * feat_b + vol.numel() * 4)
+            gL, gR = torch.empty_like(L), torch.empty_like(R)
+            add("concat_volume_bwd", cfg, time_ms(lambda: _lib.call(
+                "az_concat_volume_bwd", ops._ptr(vol), ops._ptr(gL), ops._ptr(gR), B, C, Hq, Wq, Dq, ops._stream())),
+                2 * feat_b + vol.numel() * 4)
+            del vol
+            # gwc (the volume is 8x smaller: batch it up to stay >> L2)
+            gv = ops.build_gwc_volume(L, R, Dq, G)
+            add("gwc_volume_fwd", cfg, time_ms(lambda: ops.build_gwc_volume(L, R, Dq, G), flush=True), 2 * feat_b + gv.numel() * 4)
+            add("gwc_volume_bwd", cfg, time_ms(lambda: _lib.call(
+                "az_gwc_volume_bwd", ops._ptr(gv), ops._ptr(L), ops._ptr(R), ops._ptr(gL), ops._ptr(gR), B, C, Hq, Wq,
+                Dq, G, ops._stream()), flush=True), 4 * feat_b + gv.numel() * 4)
+            del gv
+            # soft-argmin on the full-resolution logits
+            cost_bytes = 4 * D * H * W
+            Bs = max(1, min(8, int(1.6e9 // cost_bytes)))
+            cfg_s = {**cfg, "B": Bs, "int64_index": Bs * D * H * W >= 2 ** 31}
+            cost = torch.randn(Bs, D, H, W, device=DEV) * 4
+            disp, lse = torch.empty(Bs, 1, H, W, device=DEV), torch.empty(Bs, 1, H, W, device=DEV)
+            add("soft_argmin_fwd", cfg_s, time_ms(lambda: _lib.call(
+                "az_soft_argmin_fwd", ops._ptr(cost), ops._ptr(disp), ops._ptr(lse), Bs, D, H, W, ops._stream())),
+                4 * Bs * (D * H * W + H * W))
+            g = torch.randn(Bs, 1, H, W, device=DEV)
+            gcost = torch.empty_like(cost)
+            add("soft_argmin_bwd", cfg_s, time_ms(lambda: _lib.call(
+                "az_soft_argmin_bwd", ops._ptr(cost), ops._ptr(disp), ops._ptr(lse), ops._ptr(g), ops._ptr(gcost), Bs, D,
+                H, W, ops._stream())), 4 * Bs * (2 * D * H * W + 2 * H * W))
+            del cost, gcost
+    # image-sized ops at the two frame sizes (not D dependent)
+    for (H, W) in ([(544, 960)] if quick else [(256, 512), (544, 960), (1088, 1920)]):
+        B = 8
+        cfg = {"H": H, "W": W, "B": B, "ps": PS}
+        torch.manual_seed(1)
+        pL = (torch.rand(B, 1, H, W, device=DEV) > 0.5).float()
+        pR = (torch.rand(B, 1, H, W, device=DEV) > 0.5).float()
+        d = torch.rand(B, 1, H, W, device=DEV) * 64
+        mask = torch.rand(B, 1, H, W, device=DEV) > 0.2
+        hw = B * H * W
+        add("warp_fwd", cfg, time_ms(lambda: ops.warp(pR, d), flush=True), 4 * 3 * hw)
+        dg = d.clone().requires_grad_(True)
+
+        def patch_fb():
+            dg.grad = None
+            loss, _ = ops.reproj_loss(pL, pR, dg, mask, ps=PS)
+            loss.backward()
+
+        add("reproj_ps1_loss_fwd", cfg, time_ms(lambda: ops.reproj_loss(pL, pR, d, mask, ps=1), flush=True), 4 * 3 * hw + hw)
+        add("reproj_patch_loss_fwd", cfg, time_ms(lambda: ops.reproj_loss(pL, pR, d, mask, ps=PS), flush=True), 4 * 3 * hw + hw)
+        add("reproj_patch_loss_fwd+bwd", cfg, time_ms(patch_fb, flush=True), 4 * 3 * hw + hw + 3 * 4 * hw)
+        add("patch_fold", cfg, time_ms(lambda: ops.patch_fold(pR, d, PS), flush=True), 4 * 3 * hw)
+        di = (torch.rand(B, 1, H, W, device=DEV) * 64).int()
+        add("scatter_warp", cfg, time_ms(lambda: ops.scatter_warp(d, di, check_sign=False), flush=True), 4 * 3 * hw)
+        add("local_contrast_norm", cfg, time_ms(lambda: ops.local_contrast_norm(pL, 9), flush=True), 4 * 3 * hw)
+        T = 7
+        fr = torch.randint(0, 255, (B, T, H, W), dtype=torch.uint8, device=DEV)
+        add("temporal_ir", {**cfg, "T": T}, time_ms(lambda: ops.temporal_ir_pattern(fr), flush=True), T * hw + 4 * hw)
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    rows = sweep(args.quick)
+    if args.out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+        json.dump({"peak_gbs": peak(), "rows": rows}, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

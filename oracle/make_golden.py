@@ -255,11 +255,32 @@ def gen_temporal_ir():
     )
 
 
+def gen_state_dict_keys():
+    """Names and shapes of every state_dict entry of both reference PSMNet variants
+    (checkpoint compatibility contract, test.py:341-342 / train.py:155-170)."""
+    import json
+
+    ref_loader.load()
+    sys.path.insert(0, ref_loader.REFERENCE_ROOT)
+    try:
+        mods = {"psmnet": importlib.import_module("nets.psmnet.psmnet"),
+                "psmnet_3": importlib.import_module("nets.psmnet.psmnet_3")}
+    finally:
+        sys.path.remove(ref_loader.REFERENCE_ROOT)
+    out = {}
+    for name, mod in mods.items():
+        sd = mod.PSMNet(maxdisp=192).state_dict()
+        out[name] = [[k, list(v.shape)] for k, v in sd.items()]
+    with open(os.path.join(GOLDEN, "psmnet_state_dict_keys.json"), "w") as f:
+        json.dump(out, f)
+
+
 def main():
     assert ref_loader.available(), "run in the authoring container (needs /root/reference)"
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    for fn in (gen_scatter_warp, gen_temporal_ir, gen_reprojection, gen_soft_argmin, gen_psmnet_inline):
+    for fn in (gen_scatter_warp, gen_temporal_ir, gen_reprojection, gen_soft_argmin, gen_psmnet_inline,
+               gen_state_dict_keys):
         print("generating", fn.__name__, flush=True)
         fn()
     for f in sorted(os.listdir(GOLDEN)):

@@ -495,3 +495,29 @@ def test_runs_on_a_side_stream_and_counts_launches():
     s.synchronize()
     assert torch.equal(out, ref)
     assert _lib.launch_count == before + 1
+
+
+def test_int64_indexing_above_2_31_elements():
+    """BASELINE config 5 top end: [4,64,72,272,480] = 2.4e9 elements (9.6 GB) needs 64-bit
+    offsets; check the LAST pair (highest addresses) bit-exactly and the soft-argmin of a
+    [4,288,1088,1920]-sized tensor on its last image."""
+    torch.manual_seed(20)
+    L, R = torch.randn(4, 32, 272, 480, device=DEV), torch.randn(4, 32, 272, 480, device=DEV)
+    vol = ops.build_concat_volume(L, R, 72)
+    assert vol.numel() > 2 ** 31
+    assert torch.equal(vol[3:], so.concat_volume(L[3:], R[3:], 72))
+    g = torch.zeros_like(vol)
+    g[3, :, :, 100:104] = 1.0
+    gL, gR = torch.empty_like(L), torch.empty_like(R)
+    from activezero_b200 import _lib
+    _lib.call("az_concat_volume_bwd", ops._ptr(g), ops._ptr(gL), ops._ptr(gR), 4, 32, 272, 480, 72, ops._stream())
+    assert float(gL[:3].abs().max()) == 0.0 and float(gR[:3].abs().max()) == 0.0
+    x = torch.arange(480, device=DEV)
+    assert torch.equal(gL[3, 0, 101], torch.minimum(x + 1, torch.tensor(72, device=DEV)).float())
+    assert torch.equal(gR[3, 5, 102], torch.minimum(480 - x, torch.tensor(72, device=DEV)).float())
+    del vol, g
+    cost = torch.randn(4, 288, 1088, 1920, device=DEV)
+    assert cost.numel() > 2 ** 31
+    out = ops.soft_argmin(cost)
+    # outputs reach 287 here: half an fp32 ulp is already 1.5e-5
+    assert float((out[3:].double() - _sa_ref64(cost[3:, :, :, :])).abs().max()) <= 4e-5
