@@ -177,7 +177,7 @@ def time_cpu_reference(steps, warmup):
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)  # each step is a bounded 1-pair sample (~1 s)
     pairs_s, ms, cores = time_cpu_reference(steps, warmup)
     sample = f"1 pair of the {B}-pair batch per step, {steps} timed steps after {warmup} warm-up, torch {torch.__version__} CPU"
     line = {
@@ -198,17 +198,19 @@ def run_reference(args, rank):
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
 
-    from activezero_b200 import _lib, ops
+    from activezero_b200 import _lib, dist_util, ops
     from activezero_b200.utils import reprojection as az_rp
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    dist_util.init_from_env("nccl", dev)
     _lib.load()
+    # weak scaling: the job is world*B pairs, rank r owns pairs [first, first+B)
+    first_pair, n_pairs = dist_util.shard_pairs(world * B, rank, world)
+    assert n_pairs == B
 
-    host = make_inputs(B, 1000 + rank, pin=True)
+    host = make_inputs(n_pairs, 1000 + first_pair, pin=True)
     L, R, cost, pat_L, pat_R, mask = [t.to(dev, non_blocking=True) for t in host]
     torch.cuda.synchronize()
     names = ["concat_volume_fwd", "soft_argmin_fwd", "reproj_patch_loss_fwd", "patch_fold"]
@@ -290,10 +292,7 @@ def run_b200(args, rank, world, local_rank):
         ms_e2e = s2.elapsed_time(e2)
         loss_val = float(res_loss)
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
+    ms_total, ms_e2e = dist_util.max_over_ranks([ms_total, ms_e2e], dev)
 
     if rank == 0:
         per_kernel = {}
@@ -345,13 +344,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
     else:
+        args.warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
         run_b200(args, rank, world, local_rank)
 
 
