@@ -3,18 +3,34 @@
 //   vol[b,g,i,y,x] = (1/cpg) * sum_{c in group g} L[b,c,y,x] * R[b,c,y,x-i]   (x >= i, else 0)
 // with cpg = C/G.  Parity is against this repository's own torch restatement (parity unpinned).
 //
-// Same data movement as the concat volume: the forward stages the cpg left/right rows of one
-// (b, g, row-run) once (right rows as four pre-shifted copies behind a zero prefix => aligned
-// 128-bit shared loads for every disparity), then streams Dq planes of 128-bit stores; the
-// backward pulls the gradient slab into shared memory with bulk async copies and reduces it
-// gather-style (no atomics) into gL and gR.
+// Same data movement as the concat volume.  Forward: the cpg right rows of one (b, g, row-run) are
+// staged once in shared memory behind a zero prefix; a thread owns one float4 of output columns,
+// keeps its cpg left float4 in registers and sweeps the Dq planes with streaming 128-bit stores,
+// reading the shifted right window as two aligned float4 + a static register window (one LDS.128
+// per channel per four disparities).  Backward: direct 128-bit loads of the gradient planes (three
+// aligned float4 per plane: column x for gL, columns x+4m and x+4m+4 for the x+i diagonal of gR),
+// left/right rows in shared memory, fixed-order accumulation in registers: gather-style, atomic-free.
 #include "common.cuh"
 
 namespace az {
 
 constexpr int kGwcThreads = 256;
 
+// window [k, k+4) of the 8 floats (a, b), k in 1..4 static after unrolling
+__device__ __forceinline__ float4 win8(const float4& a, const float4& b, int k) {
+    switch (k) {
+        case 1: return make_float4(a.y, a.z, a.w, b.x);
+        case 2: return make_float4(a.z, a.w, b.x, b.y);
+        case 3: return make_float4(a.w, b.x, b.y, b.z);
+        default: return b;
+    }
+}
+
 // grid = (ceil(H*W/4 / 256), G, B); one float4 position per thread.
+// smem: Rs[CPG][rows_cap][pad + W], ONE copy per channel behind a zero prefix of pad >= Dq+4
+// floats.  The shift by i = 4m+r is the window [4-r, 8-r) of two aligned float4 (A at x-4m-4, B at
+// x-4m); B of step m+1 is A of step m, so each thread issues one LDS.128 per channel per FOUR
+// disparities and selects the window with static register indices.
 template <int CPG>
 __global__ void __launch_bounds__(kGwcThreads) gwc_fwd_vec4_kernel(const float* __restrict__ L,
                                                                   const float* __restrict__ R,
@@ -27,47 +43,55 @@ __global__ void __launch_bounds__(kGwcThreads) gwc_fwd_vec4_kernel(const float* 
     const int pend = min(p0 + kGwcThreads, H * W4);
     const size_t HW = (size_t)H * W;
     const int y_first = p0 / W4, y_last = (pend - 1) / W4, nrows = y_last - y_first + 1;
-    const int S = pad + W;
-    const int copy_stride = rows_cap * S;      // floats per shifted copy of one channel
-    const int ch_stride = 4 * copy_stride;     // floats per channel
+    const int S = pad + W, S4 = S >> 2, pad4 = pad >> 2;
+    const int ch_stride = rows_cap * S;
     const float* Lg = L + ((size_t)b * C + (size_t)g * CPG) * HW;
     const float* Rg = R + ((size_t)b * C + (size_t)g * CPG) * HW;
 
-    for (int t = threadIdx.x; t < CPG * copy_stride; t += kGwcThreads)
-        reinterpret_cast<float4*>(smem)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    for (int t = threadIdx.x; t < CPG * nrows * W; t += kGwcThreads) {
-        const int c = t / (nrows * W), rem = t - c * nrows * W;
-        const int y = rem / W, xx = rem - y * W;
-        const float val = __ldg(Rg + (size_t)c * HW + (size_t)(y_first + y) * W + xx);
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-            if (xx + r < W) smem[c * ch_stride + r * copy_stride + y * S + pad + xx + r] = val;
+    for (int t = threadIdx.x; t < CPG * nrows * S4; t += kGwcThreads) {
+        const int c = t / (nrows * S4), rem = t - c * nrows * S4;
+        const int y = rem / S4, q = rem - y * S4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q >= pad4)
+            v = __ldg(reinterpret_cast<const float4*>(Rg + (size_t)c * HW + (size_t)(y_first + y) * W) + (q - pad4));
+        reinterpret_cast<float4*>(smem + c * ch_stride + y * S)[q] = v;
     }
     __syncthreads();
 
     const int pp = p0 + threadIdx.x;
     if (pp >= pend) return;
     const int y = pp / W4, x = (pp - y * W4) * 4;
-    float4 l[CPG];
-#pragma unroll
-    for (int c = 0; c < CPG; ++c) l[c] = __ldg(reinterpret_cast<const float4*>(Lg + (size_t)c * HW + (size_t)pp * 4));
+    float4 l[CPG], Bw[CPG];
     const float* sp = smem + (y - y_first) * S + pad + x;
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) {
+        l[c] = __ldg(reinterpret_cast<const float4*>(Lg + (size_t)c * HW + (size_t)pp * 4));
+        Bw[c] = *reinterpret_cast<const float4*>(sp + c * ch_stride);
+    }
     float* out = vol + ((size_t)b * G + g) * Dq * HW + (size_t)pp * 4;
     const float inv = 1.0f / (float)CPG;
-    for (int i = 0; i < Dq; ++i) {
-        const float* q = sp + (i & 3) * copy_stride - (i & ~3);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m4 = 0; m4 < Dq; m4 += 4) {
+        float4 A[CPG];
 #pragma unroll
-        for (int c = 0; c < CPG; ++c) {
-            const float4 r = *reinterpret_cast<const float4*>(q + c * ch_stride);
-            acc.x = fmaf(l[c].x, r.x, acc.x);
-            acc.y = fmaf(l[c].y, r.y, acc.y);
-            acc.z = fmaf(l[c].z, r.z, acc.z);
-            acc.w = fmaf(l[c].w, r.w, acc.w);
+        for (int c = 0; c < CPG; ++c) A[c] = *reinterpret_cast<const float4*>(sp + c * ch_stride - m4 - 4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (m4 + r < Dq) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < CPG; ++c) {
+                    const float4 w = win8(A[c], Bw[c], 4 - r);
+                    acc.x = fmaf(l[c].x, w.x, acc.x);
+                    acc.y = fmaf(l[c].y, w.y, acc.y);
+                    acc.z = fmaf(l[c].z, w.z, acc.z);
+                    acc.w = fmaf(l[c].w, w.w, acc.w);
+                }
+                acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+                st_stream(reinterpret_cast<float4*>(out + (size_t)(m4 + r) * HW), acc);
+            }
         }
-        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-        st_stream(reinterpret_cast<float4*>(out + (size_t)i * HW), acc);
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) Bw[c] = A[c];
     }
 }
 
@@ -90,81 +114,111 @@ __global__ void __launch_bounds__(256) gwc_fwd_scalar_kernel(const float* __rest
     st_stream(vol + (((size_t)bg * Dq + i) * H) * W + hw, acc);
 }
 
-// ------------------------------------------------------------------------------------------
-// backward, bulk-async path: grid = (H, G, B), one image row per CTA.
-// smem: gs[Dq][W] gradient rows | Ls[cpg][W] | Rs[cpg][pad+W] (zero prefix) | mbarriers
-// gL[c,x] = inv * sum_{i<=x} g[i,x] * R[c,x-i];   gR[c,x] = inv * sum_{x+i<W} g[i,x+i] * L[c,x+i]
-// ------------------------------------------------------------------------------------------
-constexpr int kGwcBwdGroup = 8;
+// window [k, k+4) of the 8 floats (a, b), k in 0..4
+__device__ __forceinline__ float4 win8k(const float4& a, const float4& b, int k) { return k == 0 ? a : win8(a, b, k); }
 
-template <int CPG>
-__global__ void __launch_bounds__(kGwcThreads) gwc_bwd_bulk_kernel(const float* __restrict__ gvol,
-                                                                  const float* __restrict__ L,
-                                                                  const float* __restrict__ R, float* __restrict__ gL,
-                                                                  float* __restrict__ gR, int C, int H, int W, int Dq,
-                                                                  int pad) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int y = blockIdx.x, g = blockIdx.y, b = blockIdx.z, G = gridDim.y;
+__device__ __forceinline__ void fma4(float4& acc, const float4& u, const float4& v) {
+    acc.x = fmaf(u.x, v.x, acc.x);
+    acc.y = fmaf(u.y, v.y, acc.y);
+    acc.z = fmaf(u.z, v.z, acc.z);
+    acc.w = fmaf(u.w, v.w, acc.w);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, direct path (W % 4 == 0): grid = (ceil(H*W/4 / 256), G * (CPG/CPT), B).
+// A thread owns one float4 of columns for CPT channels of its group.
+//   gL[c,x] = inv * sum_{i<=x} g[i,x] * R[c,x-i];   gR[c,x] = inv * sum_{x+i<W} g[i,x+i] * L[c,x+i]
+// smem: Ls[CPT][rows_cap][W + tail] (zero tail) | Rs[CPT][rows_cap][pad + W] (zero prefix)
+// ------------------------------------------------------------------------------------------
+template <int CPG, int CPT>
+__global__ void __launch_bounds__(kGwcThreads, 2) gwc_bwd_direct_kernel(const float* __restrict__ gvol,
+                                                                       const float* __restrict__ L,
+                                                                       const float* __restrict__ R,
+                                                                       float* __restrict__ gL, float* __restrict__ gR,
+                                                                       int C, int G, int H, int W, int Dq, int pad,
+                                                                       int rows_cap) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int NCH = CPG / CPT;
+    const int W4 = W >> 2;
+    const int g = blockIdx.y / NCH, chunk = blockIdx.y - g * NCH, b = blockIdx.z;
+    const int p0 = blockIdx.x * kGwcThreads;
+    const int pend = min(p0 + kGwcThreads, H * W4);
     const size_t HW = (size_t)H * W;
-    float* gs = reinterpret_cast<float*>(smem_raw);
-    float* Ls = gs + (size_t)Dq * W;
-    float* Rs = Ls + (size_t)CPG * W;
-    const int S = pad + W;
-    const int ngroups = (Dq + kGwcBwdGroup - 1) / kGwcBwdGroup;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Rs + (size_t)CPG * S);
-    const float* gsrc = gvol + ((size_t)b * G + g) * Dq * HW + (size_t)y * W;
-    const size_t fbase = ((size_t)b * C + (size_t)g * CPG) * HW + (size_t)y * W;
+    const int y_first = p0 / W4, y_last = (pend - 1) / W4, nrows = y_last - y_first + 1;
+    const int S = pad + W, S4 = S >> 2, pad4 = pad >> 2;  // same stride for both arrays
+    const int ch_stride = rows_cap * S;
+    float* Ls = smem;
+    float* Rs = smem + CPT * ch_stride;
+    const size_t cbase = ((size_t)b * C + (size_t)g * CPG + (size_t)chunk * CPT) * HW;
 
-    if (threadIdx.x == 0) {
-        for (int q = 0; q < ngroups; ++q) mbar_init(&bars[q], 1);
-        fence_mbar_init();
-        for (int q = 0; q < ngroups; ++q) {
-            const int i0 = q * kGwcBwdGroup, cnt = min(kGwcBwdGroup, Dq - i0);
-            mbar_arrive_expect_tx(&bars[q], (uint32_t)(cnt * W * sizeof(float)));
-            for (int i = i0; i < i0 + cnt; ++i)
-                bulk_g2s(gs + (size_t)i * W, gsrc + (size_t)i * HW, (uint32_t)(W * sizeof(float)), &bars[q]);
+    for (int t = threadIdx.x; t < CPT * nrows * S4; t += kGwcThreads) {
+        const int c = t / (nrows * S4), rem = t - c * nrows * S4;
+        const int y = rem / S4, q = rem - y * S4;
+        const size_t row = cbase + (size_t)c * HW + (size_t)(y_first + y) * W;
+        float4 rv = make_float4(0.f, 0.f, 0.f, 0.f), lv = rv;
+        if (q >= pad4) rv = __ldg(reinterpret_cast<const float4*>(R + row) + (q - pad4));
+        if (q < W4) lv = __ldg(reinterpret_cast<const float4*>(L + row) + q);
+        reinterpret_cast<float4*>(Rs + c * ch_stride + y * S)[q] = rv;
+        reinterpret_cast<float4*>(Ls + c * ch_stride + y * S)[q] = lv;
+    }
+    __syncthreads();
+
+    const int pp = p0 + threadIdx.x;
+    if (pp >= pend) return;
+    const int y = pp / W4, x = (pp - y * W4) * 4;
+    const float* rp = Rs + (y - y_first) * S + pad + x;
+    const float* lp = Ls + (y - y_first) * S + x;
+    const float* gp = gvol + ((size_t)b * G + g) * Dq * HW + (size_t)pp * 4;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 aL[CPT], aR[CPT], RB[CPT], LA[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        aL[c] = zero;
+        aR[c] = zero;
+        RB[c] = *reinterpret_cast<const float4*>(rp + c * ch_stride);
+        LA[c] = *reinterpret_cast<const float4*>(lp + c * ch_stride);
+    }
+    for (int m4 = 0; m4 < Dq; m4 += 4) {
+        float4 gl[4], ga[4], gb[4];
+        const bool inA = (x + m4) < W, inB = (x + m4 + 4) < W;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = m4 + r;
+            const float* q = gp + (size_t)i * HW;
+            const bool on = i < Dq;
+            gl[r] = (on && i <= x + 3) ? __ldg(reinterpret_cast<const float4*>(q)) : zero;
+            ga[r] = (on && inA) ? __ldg(reinterpret_cast<const float4*>(q + m4)) : zero;
+            gb[r] = (on && inB) ? __ldg(reinterpret_cast<const float4*>(q + m4 + 4)) : zero;
+        }
+        float4 RA[CPT], LB[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            RA[c] = *reinterpret_cast<const float4*>(rp + c * ch_stride - m4 - 4);
+            LB[c] = *reinterpret_cast<const float4*>(lp + c * ch_stride + m4 + 4);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float4 gw = win8k(ga[r], gb[r], r);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                fma4(aL[c], gl[r], win8(RA[c], RB[c], 4 - r));
+                fma4(aR[c], gw, win8k(LA[c], LB[c], r));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            RB[c] = RA[c];
+            LA[c] = LB[c];
         }
     }
-    for (int t = threadIdx.x; t < CPG * S; t += kGwcThreads) {
-        const int c = t / S, xx = t - c * S - pad;
-        Rs[t] = xx >= 0 ? __ldg(R + fbase + (size_t)c * HW + xx) : 0.f;
-    }
-    for (int t = threadIdx.x; t < CPG * W; t += kGwcThreads) {
-        const int c = t / W, xx = t - c * W;
-        Ls[t] = __ldg(L + fbase + (size_t)c * HW + xx);
-    }
-    __syncthreads();  // Ls/Rs visible; mbarrier inits visible to the waiters
-
     const float inv = 1.0f / (float)CPG;
-    for (int x0 = 0; x0 < W; x0 += kGwcThreads) {
-        const int x = x0 + threadIdx.x;
-        float aL[CPG], aR[CPG];
 #pragma unroll
-        for (int c = 0; c < CPG; ++c) { aL[c] = 0.f; aR[c] = 0.f; }
-        for (int q = 0; q < ngroups; ++q) {
-            mbar_wait(&bars[q], 0);
-            if (x >= W) continue;
-            const int i0 = q * kGwcBwdGroup, cnt = min(kGwcBwdGroup, Dq - i0);
-            for (int i = i0; i < i0 + cnt; ++i) {
-                if (i <= x) {
-                    const float gv = gs[(size_t)i * W + x];
-#pragma unroll
-                    for (int c = 0; c < CPG; ++c) aL[c] = fmaf(gv, Rs[c * S + pad + x - i], aL[c]);
-                }
-                if (x + i < W) {
-                    const float gv = gs[(size_t)i * W + x + i];
-#pragma unroll
-                    for (int c = 0; c < CPG; ++c) aR[c] = fmaf(gv, Ls[c * W + x + i], aR[c]);
-                }
-            }
-        }
-        if (x < W) {
-#pragma unroll
-            for (int c = 0; c < CPG; ++c) {
-                if (gL != nullptr) gL[fbase + (size_t)c * HW + x] = aL[c] * inv;
-                if (gR != nullptr) gR[fbase + (size_t)c * HW + x] = aR[c] * inv;
-            }
-        }
+    for (int c = 0; c < CPT; ++c) {
+        const size_t o = cbase + (size_t)c * HW + (size_t)pp * 4;
+        if (gL != nullptr)
+            *reinterpret_cast<float4*>(gL + o) = make_float4(aL[c].x * inv, aL[c].y * inv, aL[c].z * inv, aL[c].w * inv);
+        if (gR != nullptr)
+            *reinterpret_cast<float4*>(gR + o) = make_float4(aR[c].x * inv, aR[c].y * inv, aR[c].z * inv, aR[c].w * inv);
     }
 }
 
@@ -194,9 +248,9 @@ __global__ void __launch_bounds__(256) gwc_bwd_scalar_kernel(const float* __rest
 template <int CPG>
 static int launch_gwc_fwd(const float* L, const float* R, float* vol, int B, int C, int G, int H, int W, int Dq,
                           cudaStream_t st, bool* done) {
-    const int W4 = W / 4, pad = (Dq + 3) / 4 * 4;
+    const int W4 = W / 4, pad = (Dq + 3) / 4 * 4 + 4;
     const int rows_cap = (kGwcThreads + W4 - 1) / W4 + 1;
-    const size_t smem = (size_t)CPG * 4 * rows_cap * (pad + W) * sizeof(float);
+    const size_t smem = (size_t)CPG * rows_cap * (pad + W) * sizeof(float);
     *done = false;
     if (smem > 200 * 1024) return 0;
     cudaError_t e = cudaFuncSetAttribute(gwc_fwd_vec4_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -211,17 +265,17 @@ static int launch_gwc_fwd(const float* L, const float* R, float* vol, int B, int
 template <int CPG>
 static int launch_gwc_bwd(const float* gvol, const float* L, const float* R, float* gL, float* gR, int B, int C, int G,
                           int H, int W, int Dq, cudaStream_t st, bool* done) {
-    const int pad = (Dq + 3) / 4 * 4;
-    const int ngroups = (Dq + kGwcBwdGroup - 1) / kGwcBwdGroup;
-    const size_t smem = ((size_t)Dq * W + (size_t)CPG * W + (size_t)CPG * (pad + W)) * sizeof(float) +
-                        (size_t)ngroups * sizeof(uint64_t);
+    constexpr int CPT = CPG >= 2 ? 2 : 1;
+    const int W4 = W / 4, pad = (Dq + 3) / 4 * 4 + 4;
+    const int rows_cap = (kGwcThreads + W4 - 1) / W4 + 1;
+    const size_t smem = (size_t)2 * CPT * rows_cap * (pad + W) * sizeof(float);
     *done = false;
-    if (smem > 200 * 1024) return 0;
-    cudaError_t e = cudaFuncSetAttribute(gwc_bwd_bulk_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         200 * 1024);
+    if (smem > 100 * 1024 || (long long)G * (CPG / CPT) > 65535) return 0;
+    cudaError_t e = cudaFuncSetAttribute(gwc_bwd_direct_kernel<CPG, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         100 * 1024);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid((unsigned)H, (unsigned)G, (unsigned)B);
-    gwc_bwd_bulk_kernel<CPG><<<grid, kGwcThreads, smem, st>>>(gvol, L, R, gL, gR, C, H, W, Dq, pad);
+    dim3 grid((unsigned)ceil_div((int64_t)H * W4, kGwcThreads), (unsigned)(G * (CPG / CPT)), (unsigned)B);
+    gwc_bwd_direct_kernel<CPG, CPT><<<grid, kGwcThreads, smem, st>>>(gvol, L, R, gL, gR, C, G, H, W, Dq, pad, rows_cap);
     *done = true;
     return (int)cudaGetLastError();
 }
@@ -265,7 +319,8 @@ extern "C" int az_gwc_volume_bwd(const float* gvol, const float* L, const float*
     if (!gL && !gR) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t cpg = C / G;
-    if ((W % 4 == 0) && aligned16(gvol)) {
+    if ((W % 4 == 0) && aligned16(gvol) && aligned16(L) && aligned16(R) && (!gL || aligned16(gL)) &&
+        (!gR || aligned16(gR))) {
         bool done = false;
         int rc = 0;
         switch (cpg) {

@@ -43,12 +43,14 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_fwd_kernel(const float
     const int64_t b = pix / plane, hw = pix - b * plane;
     const float* src = cost + b * D * plane + hw;
 
-    // mb = running max in the log2 domain, fl(max * log2e): the SAME rounded value is used in the
-    // exponent FMAs and in the rescale factor, so old and new partial sums stay consistent.
-    float mb[V];
+    // m = running max.  Exponents are formed as (x - m) * log2e: the subtraction is exact for the
+    // entries that carry weight (x close to m), so accuracy does not depend on the magnitude of the
+    // logits, and every rounding (term exponent, rescale exponent) is relative to a SMALL number, which
+    // keeps old and new partial sums consistent across rescales.
+    float m[V];
     double s[V], ws[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) { mb[j] = -INFINITY; s[j] = 0.0; ws[j] = 0.0; }
+    for (int j = 0; j < V; ++j) { m[j] = -INFINITY; s[j] = 0.0; ws[j] = 0.0; }
 
     for (int d0 = 0; d0 < D; d0 += kChunk) {
         float x[kChunk][V];
@@ -67,17 +69,16 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_fwd_kernel(const float
             float cm = x[0][j];
 #pragma unroll
             for (int k = 1; k < kChunk; ++k) cm = fmaxf(cm, x[k][j]);
-            const float cmb = cm * kLog2e;
-            if (cmb > mb[j]) {  // rescale the running sums (exp2(-inf) = 0 on the first chunk)
-                const double sc = (double)exp2f(mb[j] - cmb);
+            if (cm > m[j]) {  // rescale the running sums (exp2(-inf) = 0 on the first chunk)
+                const double sc = (double)exp2f((m[j] - cm) * kLog2e);
                 s[j] *= sc;
                 ws[j] *= sc;
-                mb[j] = cmb;
+                m[j] = cm;
             }
-            const float ref = (mb[j] == -INFINITY) ? 0.f : mb[j];  // leading -inf planes contribute 0
+            const float ref = (m[j] == -INFINITY) ? 0.f : m[j];  // leading -inf planes contribute 0
             float e[kChunk];
 #pragma unroll
-            for (int k = 0; k < kChunk; ++k) e[k] = exp2f(fmaf(x[k][j], kLog2e, -ref));
+            for (int k = 0; k < kChunk; ++k) e[k] = exp2f((x[k][j] - ref) * kLog2e);
             // tree sums of the chunk in fp32, running sums in fp64
             const float s01 = e[0] + e[1], s23 = e[2] + e[3], s45 = e[4] + e[5], s67 = e[6] + e[7];
             const float w01 = e[1], w23 = fmaf(e[3], 3.f, e[2] * 2.f);
@@ -93,11 +94,13 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_fwd_kernel(const float
     for (int j = 0; j < V; ++j) o[j] = (float)(ws[j] / s[j]);
     *reinterpret_cast<VT*>(disp + pix) = Vec<V>::pack(o);
     if (lse != nullptr) {
-        // saved in the log2 domain: lse2 = log2(sum_d 2^(cost_d*log2e)); the backward forms
-        // p_d = 2^(cost_d*log2e - lse2) with the same FMA as above.
+        // saved for the backward: plane 0 = max logit m, plane 1 = log2(sum_d 2^((x_d - m)*log2e));
+        // the backward forms p_d = 2^((x_d - m)*log2e - plane1) with the same exact subtraction.
+        const int64_t total = n_vec * V;
+        *reinterpret_cast<VT*>(lse + pix) = Vec<V>::pack(m);
 #pragma unroll
-        for (int j = 0; j < V; ++j) l[j] = mb[j] + log2f((float)s[j]);
-        *reinterpret_cast<VT*>(lse + pix) = Vec<V>::pack(l);
+        for (int j = 0; j < V; ++j) l[j] = log2f((float)s[j]);
+        *reinterpret_cast<VT*>(lse + total + pix) = Vec<V>::pack(l);
     }
 }
 
@@ -115,9 +118,10 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_bwd_kernel(const float
     const int64_t b = pix / plane, hw = pix - b * plane;
     const float* src = cost + b * D * plane + hw;
     float* dst = gcost + b * D * plane + hw;
-    float o[V], lb[V], g[V];
+    float o[V], mx[V], lb[V], g[V];
     Vec<V>::unpack(*reinterpret_cast<const VT*>(disp + pix), o);
-    Vec<V>::unpack(*reinterpret_cast<const VT*>(lse + pix), lb);
+    Vec<V>::unpack(*reinterpret_cast<const VT*>(lse + pix), mx);
+    Vec<V>::unpack(*reinterpret_cast<const VT*>(lse + n_vec * V + pix), lb);
     Vec<V>::unpack(*reinterpret_cast<const VT*>(gdisp + pix), g);
     for (int d0 = 0; d0 < D; d0 += kChunk) {
         VT v[kChunk];
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_bwd_kernel(const float
                 const float dd = (float)(d0 + k);
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    const float p = exp2f(fmaf(x[j], kLog2e, -lb[j]));
+                    const float p = exp2f(fmaf(x[j] - mx[j], kLog2e, -lb[j]));
                     r[j] = p * (dd - o[j]) * g[j];
                 }
                 st_stream(reinterpret_cast<VT*>(dst + (int64_t)(d0 + k) * plane), Vec<V>::pack(r));

@@ -141,7 +141,7 @@ class SoftArgminFn(torch.autograd.Function):
         B, D, H, W = c.shape
         disp = torch.empty((B, 1, H, W), dtype=torch.float32, device=c.device)
         need_bwd = ctx.needs_input_grad[0]
-        lse = torch.empty_like(disp) if need_bwd else None
+        lse = torch.empty((B, 2, H, W), dtype=torch.float32, device=c.device) if need_bwd else None
         with torch.cuda.device(c.device):
             _lib.call("az_soft_argmin_fwd", _ptr(c), _ptr(disp), _ptr(lse), B, D, H, W, _stream())
         if need_bwd:

@@ -98,7 +98,7 @@ def sweep(quick):
             Bs = max(1, min(8, int(1.6e9 // cost_bytes)))
             cfg_s = {**cfg, "B": Bs, "int64_index": Bs * D * H * W >= 2 ** 31}
             cost = torch.randn(Bs, D, H, W, device=DEV) * 4
-            disp, lse = torch.empty(Bs, 1, H, W, device=DEV), torch.empty(Bs, 1, H, W, device=DEV)
+            disp, lse = torch.empty(Bs, 1, H, W, device=DEV), torch.empty(Bs, 2, H, W, device=DEV)
             add("soft_argmin_fwd", cfg_s, time_ms(lambda: _lib.call(
                 "az_soft_argmin_fwd", ops._ptr(cost), ops._ptr(disp), ops._ptr(lse), Bs, D, H, W, ops._stream())),
                 4 * Bs * (D * H * W + H * W))

@@ -54,11 +54,12 @@ int az_gwc_volume_bwd(const float* gvol, const float* L, const float* R, float* 
 /* ---- a4/a5: soft-argmin = F.softmax(cost,1) + DisparityRegression --
  *      nets/psmnet/psmnet.py:200-201,204-205,212-217 + nets/psmnet/psmnet_submodule.py:80-89 ----
  * disp[b,0,y,x] = sum_d d * softmax_d(cost[b,:,y,x]).  cost: [B,D,H,W] LOGITS; disp: [B,1,H,W];
- * lse (optional, may be NULL): [B,1,H,W] base-2 log-sum-exp, log2(sum_d 2^(cost_d*log2(e))), saved for the
- * backward (an opaque activation shared by the two calls). */
+ * lse (optional, may be NULL): [B,2,H,W] activation saved for the backward -- for each pixel the max logit m
+ * (first B*H*W floats) and log2(sum_d 2^((cost_d - m)*log2(e))) (next B*H*W floats).  H*W*B must keep both
+ * halves 16-byte aligned for the vector path (it falls back to scalar otherwise). */
 int az_soft_argmin_fwd(const float* cost, float* disp, float* lse,
                        int64_t B, int64_t D, int64_t H, int64_t W, void* stream);
-/* gcost[b,d,y,x] = softmax_d * (d - disp) * gdisp[b,0,y,x], softmax_d = 2^(cost_d*log2(e) - lse) */
+/* gcost[b,d,y,x] = softmax_d * (d - disp) * gdisp[b,0,y,x], softmax_d = 2^((cost_d - m)*log2(e) - log2sum) */
 int az_soft_argmin_bwd(const float* cost, const float* disp, const float* lse, const float* gdisp, float* gcost,
                        int64_t B, int64_t D, int64_t H, int64_t W, void* stream);
 

@@ -27,7 +27,7 @@ T = torch.from_numpy
 def close(a, b, rtol=1e-5, floor=1e-5):
     a = a.detach().cpu().double()
     b = b.detach().cpu().double() if isinstance(b, torch.Tensor) else torch.as_tensor(b).double()
-    atol = floor * float(b.abs().max()) if b.numel() else 0.0
+    atol = floor * float(b.abs().max()) + 1e-30 if b.numel() else 0.0  # 1e-30: fp32 underflows where fp64 holds 1e-100
     err = (a - b).abs()
     tol = atol + rtol * b.abs()
     assert bool((err <= tol).all()), f"max err {float(err.max()):.3e} (atol {atol:.3e}), worst rel {float((err / (b.abs() + atol + 1e-300)).max()):.3e}"
@@ -172,6 +172,23 @@ def test_soft_argmin_fwd_bwd(shape, scale):
     out.backward(gpu(g))
     assert float((out.detach().cpu() - ref32).abs().max()) <= 1e-4  # the north-star gate vs the fp32 reference
     assert float((out.detach().cpu().double() - ref64.detach()).abs().max()) <= 2e-5  # and far inside it vs exact
+    close(cg.grad, c64.grad, rtol=1e-5, floor=1e-5)
+
+
+@pytest.mark.parametrize("scale,offset", [(1e3, 0.0), (30.0, 1e6), (1e5, -3e7)])
+def test_soft_argmin_large_magnitude_logits(scale, offset):
+    """Accuracy must not depend on the magnitude of the logits (exponents are formed from the
+    exact difference to the running max): huge / shifted logits, fwd and bwd, vs fp64."""
+    torch.manual_seed(21)
+    cost = torch.randn(1, 192, 6, 20) * scale + offset
+    c64 = cost.double().requires_grad_(True)
+    ref64 = _sa_ref64(c64)
+    g = torch.randn(ref64.shape)
+    ref64.backward(g.double())
+    cg = gpu(cost).requires_grad_(True)
+    out = ops.soft_argmin(cg)
+    out.backward(gpu(g))
+    assert float((out.detach().cpu().double() - ref64.detach()).abs().max()) <= 2e-5
     close(cg.grad, c64.grad, rtol=1e-5, floor=1e-5)
 
 
