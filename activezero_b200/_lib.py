@@ -34,6 +34,9 @@ SIGNATURES = {
     "az_gwc_volume_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "az_soft_argmin_fwd": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "az_soft_argmin_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "az_upsample_soft_argmin_fwd": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "az_upsample_soft_argmin_workspace_bytes": (_I, [_I, _I, _I, _I, _I]),
+    "az_upsample_soft_argmin_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "az_warp_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "az_warp_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "az_reproj_workspace_bytes": (_I, [_I, _I]),
@@ -47,7 +50,7 @@ SIGNATURES = {
 }
 
 # CUDA kernels enqueued by one successful call of each compute entry point
-KERNELS_PER_CALL = {"az_reproj_loss_fwd": 2, "az_temporal_ir": 3}
+KERNELS_PER_CALL = {"az_reproj_loss_fwd": 2, "az_temporal_ir": 3, "az_upsample_soft_argmin_bwd": 3}
 
 _lib = None
 launch_count = 0    # C-ABI compute calls issued

@@ -1,0 +1,470 @@
+// Trilinear upsample fused into soft-argmin (a "next" row).
+// Reference: /root/reference/nets/psmnet/psmnet.py:186-197, 208-211
+//   cost = F.interpolate(cost, (maxdisp, 4H, 4W), mode="trilinear", align_corners=False)
+// followed by :200-201 / :212-217 softmax + DisparityRegression.  The reference materialises the
+// [B,D,4H,4W] logits (401 MB per pair at 544x960, D=192) only for the soft-argmin to read them
+// back; here the kernel reads the [B,Dq,Hq,Wq] low-resolution logits (6.3 MB per pair), rebuilds
+// each full-resolution logit on the fly and reduces it immediately -- ~60x less HBM traffic, so
+// the op becomes MUFU-bound (one ex2 per full-resolution logit).
+//
+// Interpolation follows torch's upsample_trilinear3d with align_corners=False:
+//   src = max(scale*(dst+0.5)-0.5, 0), scale = in/out (float); i0 = int(src); i1 = i0 + (i0 < in-1);
+//   l1 = src - i0; l0 = 1 - l1.
+// It is separable: v_q(y,x) = bilinear_hw(lowres[q]) once per low-res plane, then
+// logit_d = l0(d)*v_{q0(d)} + l1(d)*v_{q1(d)}.
+//
+// Backward, deterministic (torch's own trilinear backward uses float atomics):
+//   1. per output pixel, G[q] = sum_d w(d,q) * p_d*(d-disp)*g      -> workspace [B,Dq,H,W]
+//   2. reduce along x with the horizontal interpolation weights     -> workspace [B,Dq,H,Wq]
+//   3. reduce along y with the vertical weights                     -> glow [B,Dq,Hq,Wq]
+#include "common.cuh"
+
+namespace az {
+
+constexpr float kLog2eU = 1.4426950408889634f;
+constexpr int kUTW = 32, kUTH = 8;  // output tile of one CTA
+
+struct Lerp {
+    int i0, i1;
+    float l0, l1;
+};
+
+__device__ __forceinline__ Lerp src_index(float scale, int dst, int in_size) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    Lerp r;
+    r.i0 = min((int)src, in_size - 1);
+    r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+    r.l1 = src - (float)r.i0;
+    r.l0 = 1.0f - r.l1;
+    return r;
+}
+
+// Shared-memory tile of the low-res logits under one output tile, and the per-thread bilinear taps.
+struct Taps {
+    int o00, o01, o10, o11;
+    float w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ float bil(const float* __restrict__ plane, const Taps& t) {
+    // torch's nesting: h0*(w0*a + w1*b) + h1*(w0*c + w1*d), folded into four products
+    return fmaf(t.w11, plane[t.o11], fmaf(t.w10, plane[t.o10], fmaf(t.w01, plane[t.o01], t.w00 * plane[t.o00])));
+}
+
+// Loads the [Dq][fh][fw] footprint of this CTA's output tile; returns the tile origin.
+__device__ __forceinline__ void load_tile(const float* __restrict__ low, float* __restrict__ tile, int b, int Dq, int Hq,
+                                          int Wq, int h_lo, int w_lo, int fh, int fw, int FHW) {
+    const int n = Dq * fh * fw;
+    for (int t = threadIdx.y * kUTW + threadIdx.x; t < n; t += kUTW * kUTH) {
+        const int q = t / (fh * fw), rem = t - q * fh * fw;
+        const int hh = rem / fw, ww = rem - hh * fw;
+        tile[q * FHW + hh * fw + ww] =
+            __ldg(low + (((size_t)b * Dq + q) * Hq + (h_lo + hh)) * Wq + (w_lo + ww));
+    }
+}
+
+// Depth look-up tables shared by the CTA: l1[d] = weight of plane q1(d); dstart[q] = first d whose
+// lower plane is q (dstart[Dq] = D).  Upsampling => q0(d) is non-decreasing with steps <= 1, so the
+// d axis splits into Dq consecutive intervals, on each of which the logit is a monotone lerp
+// between v_q and v_{q1} -- its maximum is attained at the interval's first or last sample.
+__device__ __forceinline__ void build_depth_lut(float* __restrict__ l1, int* __restrict__ dstart, float sd, int Dq, int D) {
+    const int tid = threadIdx.y * kUTW + threadIdx.x;
+    for (int d = tid; d < D; d += kUTW * kUTH) {
+        const Lerp ld = src_index(sd, d, Dq);
+        l1[d] = ld.l1;
+        if (d == 0 || src_index(sd, d - 1, Dq).i0 != ld.i0) dstart[ld.i0] = d;
+    }
+    if (tid == 0) dstart[Dq] = D;
+}
+
+// grid = (ceil(W/32), ceil(H/8), B), block = (32, 8)
+// smem: tile[Dq*FHW] floats | l1[D] floats | dstart[Dq+1] ints
+__global__ void __launch_bounds__(kUTW * kUTH) upsample_soft_argmin_fwd_kernel(
+    const float* __restrict__ low, float* __restrict__ disp, float* __restrict__ stats, int Dq, int Hq, int Wq, int D,
+    int H, int W, float sd, float sh, float sw, int FHW, int64_t total) {
+    extern __shared__ float tile[];
+    float* l1 = tile + (size_t)Dq * FHW;
+    int* dstart = reinterpret_cast<int*>(l1 + D);
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * kUTW, y0 = blockIdx.y * kUTH;
+    const int x1 = min(x0 + kUTW, W) - 1, y1 = min(y0 + kUTH, H) - 1;
+    const int h_lo = src_index(sh, y0, Hq).i0, h_hi = src_index(sh, y1, Hq).i1;
+    const int w_lo = src_index(sw, x0, Wq).i0, w_hi = src_index(sw, x1, Wq).i1;
+    const int fh = h_hi - h_lo + 1, fw = w_hi - w_lo + 1;
+    load_tile(low, tile, b, Dq, Hq, Wq, h_lo, w_lo, fh, fw, FHW);
+    build_depth_lut(l1, dstart, sd, Dq, D);
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const Lerp ly = src_index(sh, y, Hq), lx = src_index(sw, x, Wq);
+    Taps t;
+    t.o00 = (ly.i0 - h_lo) * fw + (lx.i0 - w_lo);
+    t.o01 = (ly.i0 - h_lo) * fw + (lx.i1 - w_lo);
+    t.o10 = (ly.i1 - h_lo) * fw + (lx.i0 - w_lo);
+    t.o11 = (ly.i1 - h_lo) * fw + (lx.i1 - w_lo);
+    t.w00 = ly.l0 * lx.l0; t.w01 = ly.l0 * lx.l1; t.w10 = ly.l1 * lx.l0; t.w11 = ly.l1 * lx.l1;
+
+    // online softmax over the Dq depth intervals; interval sums in fp32, running sums in fp64
+    float m = -INFINITY;
+    double s = 0.0, ws = 0.0;
+    float va = bil(tile, t);
+    for (int q = 0; q < Dq; ++q) {
+        const float vb = (q + 1 < Dq) ? bil(tile + (q + 1) * FHW, t) : va;
+        const float diff = vb - va;
+        const int db = dstart[q], de = dstart[q + 1];
+        if (de > db) {
+            const float lf = fmaf(l1[db], diff, va), ll = fmaf(l1[de - 1], diff, va);
+            const float cm = fmaxf(lf, ll);
+            if (cm > m) {
+                const double sc = (double)exp2f((m - cm) * kLog2eU);
+                s *= sc;
+                ws *= sc;
+                m = cm;
+            }
+            float cs = 0.f, cw = 0.f, kf = 0.f;
+            for (int d = db; d < de; ++d) {
+                const float e = exp2f((fmaf(l1[d], diff, va) - m) * kLog2eU);
+                cs += e;
+                cw = fmaf(kf, e, cw);
+                kf += 1.0f;
+            }
+            s += (double)cs;
+            ws += (double)cw + (double)db * (double)cs;
+        }
+        va = vb;
+    }
+    const size_t pix = ((size_t)b * H + y) * W + x;
+    disp[pix] = (float)(ws / s);
+    if (stats != nullptr) {
+        stats[pix] = m;
+        stats[total + pix] = log2f((float)s);
+    }
+}
+
+// backward stage 1: per-pixel gradient w.r.t. the Dq interpolated planes v_q(y,x).  G: [B,Dq,H,W]
+__global__ void __launch_bounds__(kUTW * kUTH) upsample_soft_argmin_bwd_pix_kernel(
+    const float* __restrict__ low, const float* __restrict__ disp, const float* __restrict__ stats,
+    const float* __restrict__ gdisp, float* __restrict__ G, int Dq, int Hq, int Wq, int D, int H, int W, float sd,
+    float sh, float sw, int FHW, int64_t total) {
+    extern __shared__ float tile[];
+    float* l1 = tile + (size_t)Dq * FHW;
+    int* dstart = reinterpret_cast<int*>(l1 + D);
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * kUTW, y0 = blockIdx.y * kUTH;
+    const int x1 = min(x0 + kUTW, W) - 1, y1 = min(y0 + kUTH, H) - 1;
+    const int h_lo = src_index(sh, y0, Hq).i0, h_hi = src_index(sh, y1, Hq).i1;
+    const int w_lo = src_index(sw, x0, Wq).i0, w_hi = src_index(sw, x1, Wq).i1;
+    const int fh = h_hi - h_lo + 1, fw = w_hi - w_lo + 1;
+    load_tile(low, tile, b, Dq, Hq, Wq, h_lo, w_lo, fh, fw, FHW);
+    build_depth_lut(l1, dstart, sd, Dq, D);
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const Lerp ly = src_index(sh, y, Hq), lx = src_index(sw, x, Wq);
+    Taps t;
+    t.o00 = (ly.i0 - h_lo) * fw + (lx.i0 - w_lo);
+    t.o01 = (ly.i0 - h_lo) * fw + (lx.i1 - w_lo);
+    t.o10 = (ly.i1 - h_lo) * fw + (lx.i0 - w_lo);
+    t.o11 = (ly.i1 - h_lo) * fw + (lx.i1 - w_lo);
+    t.w00 = ly.l0 * lx.l0; t.w01 = ly.l0 * lx.l1; t.w10 = ly.l1 * lx.l0; t.w11 = ly.l1 * lx.l1;
+
+    const size_t pix = ((size_t)b * H + y) * W + x;
+    const float m = stats[pix], l2s = stats[total + pix], out = disp[pix], g = gdisp[pix];
+    const size_t HW = (size_t)H * W;
+    float* Gp = G + (size_t)b * Dq * HW + (size_t)y * W + x;
+    float va = bil(tile, t);
+    float carry = 0.f;  // gradient already collected for plane q as the UPPER plane of interval q-1
+    for (int q = 0; q < Dq; ++q) {
+        const bool top = q + 1 >= Dq;
+        const float vb = top ? va : bil(tile + (q + 1) * FHW, t);
+        const float diff = vb - va;
+        const int db = dstart[q], de = dstart[q + 1];
+        float ga = 0.f, gb = 0.f, df = (float)db;
+        for (int d = db; d < de; ++d) {
+            const float w1 = l1[d];
+            const float p = exp2f(fmaf(fmaf(w1, diff, va) - m, kLog2eU, -l2s));
+            const float gc = p * (df - out) * g;
+            gb = fmaf(w1, gc, gb);
+            ga += gc;
+            df += 1.0f;
+        }
+        ga -= gb;  // sum (1 - w1) * gc
+        Gp[(size_t)q * HW] = carry + (top ? ga + gb : ga);
+        carry = gb;
+        va = vb;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Depth scale exactly 4 (D == 4*Dq, the only case PSMNet uses: psmnet.py:186-211).  The depth
+// weights are then the constants {1/8, 3/8, 5/8, 7/8} (exact in binary): interval q covers
+// d = 4q+2 .. 4q+5; d = 0,1 clamp to plane 0 and d = D-2, D-1 clamp to plane Dq-1.  The four
+// samples of an interval are unrolled with immediate weights -- no look-up tables, no inner
+// loop: ~45 instructions and 4 ex2 per interval.
+// ------------------------------------------------------------------------------------------
+struct TileGeom {
+    int h_lo, w_lo, fh, fw;
+};
+
+__device__ __forceinline__ TileGeom tile_geom(float sh, float sw, int Hq, int Wq, int H, int W) {
+    const int x0 = blockIdx.x * kUTW, y0 = blockIdx.y * kUTH;
+    const int x1 = min(x0 + kUTW, W) - 1, y1 = min(y0 + kUTH, H) - 1;
+    TileGeom g;
+    g.h_lo = src_index(sh, y0, Hq).i0;
+    g.w_lo = src_index(sw, x0, Wq).i0;
+    g.fh = src_index(sh, y1, Hq).i1 - g.h_lo + 1;
+    g.fw = src_index(sw, x1, Wq).i1 - g.w_lo + 1;
+    return g;
+}
+
+__device__ __forceinline__ Taps make_taps(float sh, float sw, int y, int x, int Hq, int Wq, const TileGeom& g) {
+    const Lerp ly = src_index(sh, y, Hq), lx = src_index(sw, x, Wq);
+    Taps t;
+    t.o00 = (ly.i0 - g.h_lo) * g.fw + (lx.i0 - g.w_lo);
+    t.o01 = (ly.i0 - g.h_lo) * g.fw + (lx.i1 - g.w_lo);
+    t.o10 = (ly.i1 - g.h_lo) * g.fw + (lx.i0 - g.w_lo);
+    t.o11 = (ly.i1 - g.h_lo) * g.fw + (lx.i1 - g.w_lo);
+    t.w00 = ly.l0 * lx.l0; t.w01 = ly.l0 * lx.l1; t.w10 = ly.l1 * lx.l0; t.w11 = ly.l1 * lx.l1;
+    return t;
+}
+
+__global__ void __launch_bounds__(kUTW * kUTH) upsample4_soft_argmin_fwd_kernel(
+    const float* __restrict__ low, float* __restrict__ disp, float* __restrict__ stats, int Dq, int Hq, int Wq, int H,
+    int W, float sh, float sw, int FHW, int64_t total) {
+    extern __shared__ float tile[];
+    const int b = blockIdx.z;
+    const TileGeom tg = tile_geom(sh, sw, Hq, Wq, H, W);
+    load_tile(low, tile, b, Dq, Hq, Wq, tg.h_lo, tg.w_lo, tg.fh, tg.fw, FHW);
+    __syncthreads();
+    const int x = blockIdx.x * kUTW + threadIdx.x, y = blockIdx.y * kUTH + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const Taps t = make_taps(sh, sw, y, x, Hq, Wq, tg);
+    const int D = 4 * Dq;
+
+    float va = bil(tile, t);
+    float m = va;                  // d = 0, 1 sample plane 0 exactly
+    double s = 2.0, ws = 1.0;      // e = 1 at d = 0 and d = 1
+    const float* pl = tile;
+    for (int q = 0; q + 1 < Dq; ++q) {
+        pl += FHW;
+        const float vb = bil(pl, t);
+        const float diff = vb - va;
+        const float l0 = fmaf(0.125f, diff, va), l1 = fmaf(0.375f, diff, va);
+        const float l2 = fmaf(0.625f, diff, va), l3 = fmaf(0.875f, diff, va);
+        const float cm = fmaxf(l0, l3);
+        if (cm > m) {
+            const double sc = (double)exp2f((m - cm) * kLog2eU);
+            s *= sc;
+            ws *= sc;
+            m = cm;
+        }
+        const float e0 = exp2f((l0 - m) * kLog2eU), e1 = exp2f((l1 - m) * kLog2eU);
+        const float e2 = exp2f((l2 - m) * kLog2eU), e3 = exp2f((l3 - m) * kLog2eU);
+        const float es = (e0 + e1) + (e2 + e3);
+        const float ew = fmaf(3.0f, e3, fmaf(2.0f, e2, e1));
+        s += (double)es;
+        ws += fma((double)(4 * q + 2), (double)es, (double)ew);
+        va = vb;
+    }
+    {   // d = D-2, D-1 sample plane Dq-1 exactly
+        if (va > m) {
+            const double sc = (double)exp2f((m - va) * kLog2eU);
+            s *= sc;
+            ws *= sc;
+            m = va;
+        }
+        const double e = (double)exp2f((va - m) * kLog2eU);
+        s += 2.0 * e;
+        ws += e * (double)(2 * D - 3);
+    }
+    const size_t pix = ((size_t)b * H + y) * W + x;
+    disp[pix] = (float)(ws / s);
+    if (stats != nullptr) {
+        stats[pix] = m;
+        stats[total + pix] = log2f((float)s);
+    }
+}
+
+__global__ void __launch_bounds__(kUTW * kUTH) upsample4_soft_argmin_bwd_pix_kernel(
+    const float* __restrict__ low, const float* __restrict__ disp, const float* __restrict__ stats,
+    const float* __restrict__ gdisp, float* __restrict__ G, int Dq, int Hq, int Wq, int H, int W, float sh, float sw,
+    int FHW, int64_t total) {
+    extern __shared__ float tile[];
+    const int b = blockIdx.z;
+    const TileGeom tg = tile_geom(sh, sw, Hq, Wq, H, W);
+    load_tile(low, tile, b, Dq, Hq, Wq, tg.h_lo, tg.w_lo, tg.fh, tg.fw, FHW);
+    __syncthreads();
+    const int x = blockIdx.x * kUTW + threadIdx.x, y = blockIdx.y * kUTH + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const Taps t = make_taps(sh, sw, y, x, Hq, Wq, tg);
+    const int D = 4 * Dq;
+    const size_t pix = ((size_t)b * H + y) * W + x;
+    const float m = stats[pix], l2s = stats[total + pix], out = disp[pix], g = gdisp[pix];
+    const size_t HW = (size_t)H * W;
+    float* Gp = G + (size_t)b * Dq * HW + (size_t)y * W + x;
+
+    float va = bil(tile, t);
+    // d = 0, 1 -> plane 0 with weight 1
+    float carry;
+    {
+        const float p = exp2f(fmaf(va - m, kLog2eU, -l2s));
+        carry = p * g * ((0.0f - out) + (1.0f - out));
+    }
+    const float* pl = tile;
+    for (int q = 0; q + 1 < Dq; ++q) {
+        pl += FHW;
+        const float vb = bil(pl, t);
+        const float diff = vb - va;
+        const float bo = (float)(4 * q + 2) - out;
+        const float p0 = exp2f(fmaf(fmaf(0.125f, diff, va) - m, kLog2eU, -l2s));
+        const float p1 = exp2f(fmaf(fmaf(0.375f, diff, va) - m, kLog2eU, -l2s));
+        const float p2 = exp2f(fmaf(fmaf(0.625f, diff, va) - m, kLog2eU, -l2s));
+        const float p3 = exp2f(fmaf(fmaf(0.875f, diff, va) - m, kLog2eU, -l2s));
+        const float g0 = p0 * (bo * g), g1 = p1 * ((bo + 1.0f) * g);
+        const float g2 = p2 * ((bo + 2.0f) * g), g3 = p3 * ((bo + 3.0f) * g);
+        const float gb = fmaf(0.875f, g3, fmaf(0.625f, g2, fmaf(0.375f, g1, 0.125f * g0)));
+        const float gs = (g0 + g1) + (g2 + g3);
+        Gp[(size_t)q * HW] = carry + (gs - gb);
+        carry = gb;
+        va = vb;
+    }
+    {   // d = D-2, D-1 -> plane Dq-1 with weight 1
+        const float p = exp2f(fmaf(va - m, kLog2eU, -l2s));
+        Gp[(size_t)(Dq - 1) * HW] = carry + p * g * (((float)(D - 2) - out) + ((float)(D - 1) - out));
+    }
+}
+
+// backward stage 2: T[b,q,y,w] = sum_x wx(x,w) * G[b,q,y,x].   grid = (ceil(Wq/128), H, B*Dq)
+__global__ void __launch_bounds__(128) upsample_bwd_reduce_x_kernel(const float* __restrict__ G, float* __restrict__ T,
+                                                                   int H, int W, int Wq, float sw) {
+    const int w = blockIdx.x * 128 + threadIdx.x;
+    if (w >= Wq) return;
+    const size_t row = (size_t)blockIdx.z * H + blockIdx.y;
+    const float* g = G + row * W;
+    // output columns whose source index can touch w: src(x) in (w-1, w+1)
+    const float inv = 1.0f / sw;
+    int xlo = (int)floorf(((float)w - 1.0f + 0.5f) * inv - 0.5f) - 1;
+    int xhi = (int)ceilf(((float)w + 1.0f + 0.5f) * inv - 0.5f) + 1;
+    xlo = max(xlo, 0);
+    xhi = min(xhi, W - 1);
+    float acc = 0.f;
+    for (int x = xlo; x <= xhi; ++x) {
+        const Lerp l = src_index(sw, x, Wq);
+        float wt = 0.f;
+        if (l.i0 == w) wt += l.l0;
+        if (l.i1 == w) wt += l.l1;
+        if (wt != 0.f) acc = fmaf(wt, __ldg(g + x), acc);
+    }
+    T[row * Wq + w] = acc;
+}
+
+// backward stage 3: glow[b,q,h,w] = sum_y wy(y,h) * T[b,q,y,w].   grid = (ceil(Wq/128), Hq, B*Dq)
+__global__ void __launch_bounds__(128) upsample_bwd_reduce_y_kernel(const float* __restrict__ T, float* __restrict__ glow,
+                                                                   int H, int Hq, int Wq, float sh) {
+    const int w = blockIdx.x * 128 + threadIdx.x;
+    if (w >= Wq) return;
+    const int h = blockIdx.y;
+    const size_t plane = blockIdx.z;
+    const float inv = 1.0f / sh;
+    int ylo = (int)floorf(((float)h - 1.0f + 0.5f) * inv - 0.5f) - 1;
+    int yhi = (int)ceilf(((float)h + 1.0f + 0.5f) * inv - 0.5f) + 1;
+    ylo = max(ylo, 0);
+    yhi = min(yhi, H - 1);
+    float acc = 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+        const Lerp l = src_index(sh, y, Hq);
+        float wt = 0.f;
+        if (l.i0 == h) wt += l.l0;
+        if (l.i1 == h) wt += l.l1;
+        if (wt != 0.f) acc = fmaf(wt, __ldg(T + (plane * H + y) * Wq + w), acc);
+    }
+    glow[(plane * Hq + h) * Wq + w] = acc;
+}
+
+static int tile_extent(int in_size, int out_size, int tile) {
+    // max number of low-res indices under `tile` consecutive outputs (+1 for the i1 neighbour)
+    const double scale = (double)in_size / out_size;
+    int e = (int)(tile * scale) + 3;
+    return e < in_size ? e : in_size;
+}
+
+}  // namespace az
+
+using namespace az;
+
+extern "C" int64_t az_upsample_soft_argmin_workspace_bytes(int64_t B, int64_t Dq, int64_t H, int64_t W, int64_t Wq) {
+    return B * Dq * H * (W + Wq) * (int64_t)sizeof(float);
+}
+
+static int upsample_args_ok(int64_t B, int64_t Dq, int64_t Hq, int64_t Wq, int64_t D, int64_t H, int64_t W) {
+    if (B <= 0 || Dq <= 0 || Hq <= 0 || Wq <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    if (D < Dq || H < Hq || W < Wq) return 0;  // upsampling only
+    if (B > 65535 || H > 65535 || B * Dq > 65535 || H * W >= (1ll << 31)) return 0;
+    return 1;
+}
+
+extern "C" int az_upsample_soft_argmin_fwd(const float* lowres, float* disp, float* stats, int64_t B, int64_t Dq,
+                                           int64_t Hq, int64_t Wq, int64_t D, int64_t H, int64_t W, void* stream) {
+    if (!lowres || !disp || !upsample_args_ok(B, Dq, Hq, Wq, D, H, W)) return AZ_ERR_BAD_ARG;
+    const int fh = tile_extent((int)Hq, (int)H, kUTH), fw = tile_extent((int)Wq, (int)W, kUTW);
+    const int FHW = fh * fw;
+    const size_t smem = ((size_t)Dq * FHW + D + Dq + 1) * sizeof(float);
+    if (smem > 200 * 1024) return AZ_ERR_BAD_ARG;
+    cudaError_t e = cudaFuncSetAttribute(upsample_soft_argmin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)ceil_div(W, kUTW), (unsigned)ceil_div(H, kUTH), (unsigned)B);
+    if (D == 4 * Dq && Dq >= 2) {
+        e = cudaFuncSetAttribute(upsample4_soft_argmin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        upsample4_soft_argmin_fwd_kernel<<<grid, dim3(kUTW, kUTH), smem, (cudaStream_t)stream>>>(
+            lowres, disp, stats, (int)Dq, (int)Hq, (int)Wq, (int)H, (int)W, (float)Hq / (float)H, (float)Wq / (float)W,
+            FHW, B * H * W);
+        AZ_LAUNCH_CHECK();
+        return 0;
+    }
+    upsample_soft_argmin_fwd_kernel<<<grid, dim3(kUTW, kUTH), smem, (cudaStream_t)stream>>>(
+        lowres, disp, stats, (int)Dq, (int)Hq, (int)Wq, (int)D, (int)H, (int)W, (float)Dq / (float)D,
+        (float)Hq / (float)H, (float)Wq / (float)W, FHW, B * H * W);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int az_upsample_soft_argmin_bwd(const float* lowres, const float* disp, const float* stats,
+                                           const float* gdisp, float* glow, void* workspace, int64_t B, int64_t Dq,
+                                           int64_t Hq, int64_t Wq, int64_t D, int64_t H, int64_t W, void* stream) {
+    if (!lowres || !disp || !stats || !gdisp || !glow || !workspace || !upsample_args_ok(B, Dq, Hq, Wq, D, H, W))
+        return AZ_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int fh = tile_extent((int)Hq, (int)H, kUTH), fw = tile_extent((int)Wq, (int)W, kUTW);
+    const int FHW = fh * fw;
+    const size_t smem = ((size_t)Dq * FHW + D + Dq + 1) * sizeof(float);
+    if (smem > 200 * 1024) return AZ_ERR_BAD_ARG;
+    cudaError_t e = cudaFuncSetAttribute(upsample_soft_argmin_bwd_pix_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    float* G = (float*)workspace;
+    float* T = G + B * Dq * H * W;
+    const float sd = (float)Dq / (float)D, sh = (float)Hq / (float)H, sw = (float)Wq / (float)W;
+    dim3 grid((unsigned)ceil_div(W, kUTW), (unsigned)ceil_div(H, kUTH), (unsigned)B);
+    if (D == 4 * Dq && Dq >= 2) {
+        e = cudaFuncSetAttribute(upsample4_soft_argmin_bwd_pix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        upsample4_soft_argmin_bwd_pix_kernel<<<grid, dim3(kUTW, kUTH), smem, st>>>(
+            lowres, disp, stats, gdisp, G, (int)Dq, (int)Hq, (int)Wq, (int)H, (int)W, sh, sw, FHW, B * H * W);
+    } else {
+        upsample_soft_argmin_bwd_pix_kernel<<<grid, dim3(kUTW, kUTH), smem, st>>>(
+            lowres, disp, stats, gdisp, G, (int)Dq, (int)Hq, (int)Wq, (int)D, (int)H, (int)W, sd, sh, sw, FHW,
+            B * H * W);
+    }
+    AZ_LAUNCH_CHECK();
+    dim3 gx((unsigned)ceil_div(Wq, 128), (unsigned)H, (unsigned)(B * Dq));
+    upsample_bwd_reduce_x_kernel<<<gx, 128, 0, st>>>(G, T, (int)H, (int)W, (int)Wq, sw);
+    AZ_LAUNCH_CHECK();
+    dim3 gy((unsigned)ceil_div(Wq, 128), (unsigned)Hq, (unsigned)(B * Dq));
+    upsample_bwd_reduce_y_kernel<<<gy, 128, 0, st>>>(T, glow, (int)H, (int)Hq, (int)Wq, sh);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}

@@ -131,6 +131,9 @@ class PSMNetBase(nn.Module):
     def __init__(self, feature_extraction: nn.Module, maxdisp: int = 192):
         super().__init__()
         self.maxdisp = maxdisp
+        # False = the reference's dataflow (F.interpolate then soft-argmin on the 401 MB logits);
+        # True = the fused upsample+soft-argmin kernel (same result to <= 1e-4 px).
+        self.fuse_upsample = False
         self.feature_extraction = feature_extraction
         self.dres0 = nn.Sequential(convbn_3d(64, 32, 3, 1, 1), nn.ReLU(inplace=True),
                                    convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True))
@@ -178,6 +181,9 @@ class PSMNetBase(nn.Module):
         fused soft-argmin (replaces softmax + DisparityRegression)."""
         from ... import ops
 
+        if self.fuse_upsample:
+            # SURVEY.md §8f rank 1: never materialise the [B,maxdisp,4H,4W] logits
+            return ops.upsample_soft_argmin(cost, (self.maxdisp, 4 * H, 4 * W))
         up = F.interpolate(cost, (self.maxdisp, 4 * H, 4 * W), mode="trilinear", align_corners=False)
         return ops.soft_argmin(torch.squeeze(up, 1))
 

@@ -165,6 +165,51 @@ def soft_argmin(cost):
     return SoftArgminFn.apply(cost)
 
 
+class UpsampleSoftArgminFn(torch.autograd.Function):
+    """F.interpolate(cost, (D,H,W), 'trilinear', align_corners=False) -> squeeze ->
+    softmax -> DisparityRegression (psmnet.py:186-217) in one kernel that reads the
+    low-resolution logits only."""
+
+    @staticmethod
+    def forward(ctx, lowres, out_size):
+        c = _cuda_f32(lowres, "lowres")
+        if c.dim() == 5:
+            if c.shape[1] != 1:
+                raise ValueError("upsample_soft_argmin: expected [B,1,Dq,Hq,Wq]")
+        elif c.dim() != 4:
+            raise ValueError("upsample_soft_argmin: expected [B,1,Dq,Hq,Wq] or [B,Dq,Hq,Wq]")
+        B, Dq, Hq, Wq = c.shape[0], c.shape[-3], c.shape[-2], c.shape[-1]
+        D, H, W = (int(v) for v in out_size)
+        disp = torch.empty((B, 1, H, W), dtype=torch.float32, device=c.device)
+        need_bwd = ctx.needs_input_grad[0]
+        stats = torch.empty((B, 2, H, W), dtype=torch.float32, device=c.device) if need_bwd else None
+        with torch.cuda.device(c.device):
+            _lib.call("az_upsample_soft_argmin_fwd", _ptr(c), _ptr(disp), _ptr(stats), B, Dq, Hq, Wq, D, H, W, _stream())
+        if need_bwd:
+            ctx.save_for_backward(c, disp, stats)
+        ctx.dims = (B, Dq, Hq, Wq, D, H, W)
+        return disp
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gdisp):
+        c, disp, stats = ctx.saved_tensors
+        B, Dq, Hq, Wq, D, H, W = ctx.dims
+        g = _cuda_f32(gdisp, "grad_disp")
+        glow = torch.empty_like(c)
+        ws = torch.empty((_lib.query("az_upsample_soft_argmin_workspace_bytes", B, Dq, H, W, Wq),), dtype=torch.uint8,
+                         device=c.device)
+        with torch.cuda.device(c.device):
+            _lib.call("az_upsample_soft_argmin_bwd", _ptr(c), _ptr(disp), _ptr(stats), _ptr(g), _ptr(glow), _ptr(ws),
+                      B, Dq, Hq, Wq, D, H, W, _stream())
+        return glow, None
+
+
+def upsample_soft_argmin(lowres, out_size):
+    """[B,1,Dq,Hq,Wq] low-res logits -> [B,1,H,W] disparity for out_size = (D,H,W)."""
+    return UpsampleSoftArgminFn.apply(lowres, tuple(out_size))
+
+
 # ----------------------------------------------------------------------------
 # a6 bilinear disparity warp
 # ----------------------------------------------------------------------------

@@ -108,6 +108,32 @@ def sweep(quick):
                 "az_soft_argmin_bwd", ops._ptr(cost), ops._ptr(disp), ops._ptr(lse), ops._ptr(g), ops._ptr(gcost), Bs, D,
                 H, W, ops._stream())), 4 * Bs * (2 * D * H * W + 2 * H * W))
             del cost, gcost
+            # fused trilinear upsample + soft-argmin: reads the low-res logits only
+            low = torch.randn(Bs, 1, Dq, Hq, Wq, device=DEV) * 4
+            add("upsample_soft_argmin_fwd", cfg_s, time_ms(lambda: ops.upsample_soft_argmin(low, (D, H, W)), flush=True),
+                4 * Bs * (Dq * Hq * Wq + H * W))
+            lowg = low.clone().requires_grad_(True)
+
+            def fused_fb():
+                lowg.grad = None
+                ops.upsample_soft_argmin(lowg, (D, H, W)).backward(g)
+
+            add("upsample_soft_argmin_fwd+bwd", cfg_s, time_ms(fused_fb, flush=True),
+                4 * Bs * (2 * Dq * Hq * Wq + 4 * H * W))
+            # context: the reference dataflow for one head on the GPU (stock torch trilinear
+            # interpolate materialising the logits, then this repo's soft-argmin)
+            import torch.nn.functional as F
+
+            def unfused_f():
+                return ops.soft_argmin(torch.squeeze(F.interpolate(low, (D, H, W), mode="trilinear", align_corners=False), 1))
+
+            def unfused_fb():
+                lowg.grad = None
+                ops.soft_argmin(torch.squeeze(F.interpolate(lowg, (D, H, W), mode="trilinear", align_corners=False), 1)).backward(g)
+
+            add("context:torch_interpolate+soft_argmin_fwd", cfg_s, time_ms(unfused_f), 4 * Bs * (2 * D * H * W + H * W))
+            add("context:torch_interpolate+soft_argmin_fwd+bwd", cfg_s, time_ms(unfused_fb), 4 * Bs * (6 * D * H * W))
+            del low, lowg
     # image-sized ops at the two frame sizes (not D dependent)
     for (H, W) in ([(544, 960)] if quick else [(256, 512), (544, 960), (1088, 1920)]):
         B = 8

@@ -63,6 +63,21 @@ int az_soft_argmin_fwd(const float* cost, float* disp, float* lse,
 int az_soft_argmin_bwd(const float* cost, const float* disp, const float* lse, const float* gdisp, float* gcost,
                        int64_t B, int64_t D, int64_t H, int64_t W, void* stream);
 
+/* ---- trilinear upsample fused into soft-argmin --
+ *      nets/psmnet/psmnet.py:186-197,208-211 (F.interpolate(cost,(D,4H,4W),'trilinear',align_corners=False))
+ *      followed by the soft-argmin above, without materialising the [B,D,H,W] logits.
+ * lowres: [B,1,Dq,Hq,Wq] (= [B,Dq,Hq,Wq]); disp: [B,1,H,W]; stats (optional): [B,2,H,W] saved for the backward;
+ * (D,H,W) is the output size (upsampling only: D >= Dq, H >= Hq, W >= Wq). */
+int az_upsample_soft_argmin_fwd(const float* lowres, float* disp, float* stats,
+                                int64_t B, int64_t Dq, int64_t Hq, int64_t Wq,
+                                int64_t D, int64_t H, int64_t W, void* stream);
+/* glow: [B,1,Dq,Hq,Wq], fully written (deterministic gather, no atomics);
+ * workspace: az_upsample_soft_argmin_workspace_bytes(B,Dq,H,W,Wq) bytes. */
+int64_t az_upsample_soft_argmin_workspace_bytes(int64_t B, int64_t Dq, int64_t H, int64_t W, int64_t Wq);
+int az_upsample_soft_argmin_bwd(const float* lowres, const float* disp, const float* stats, const float* gdisp,
+                                float* glow, void* workspace, int64_t B, int64_t Dq, int64_t Hq, int64_t Wq,
+                                int64_t D, int64_t H, int64_t W, void* stream);
+
 /* ---- a6: bilinear disparity warp -- utils/reprojection.py:13-35 (apply_disparity) ----
  * out[b,c,i,j] = bilinear2D(img[b,c]; xs, ys), zeros padding, align_corners=False, with the reference's
  * fp32 op order: f = lin_x[j] + disp/W; g = 2f-1; xs = ((g+1)*W-1)/2 (same for y with lin_y[i], H).

@@ -538,3 +538,69 @@ def test_int64_indexing_above_2_31_elements():
     out = ops.soft_argmin(cost)
     # outputs reach 287 here: half an fp32 ulp is already 1.5e-5
     assert float((out[3:].double() - _sa_ref64(cost[3:, :, :, :])).abs().max()) <= 4e-5
+
+
+# --------------------------------------------------------------------------- §8f-1 fused upsample + soft-argmin
+def _upsample_ref(low, size, dtype=torch.float32):
+    """psmnet.py:186-217 for one head, restated with the oracle's soft-argmin."""
+    up = torch.nn.functional.interpolate(low.to(dtype), size, mode="trilinear", align_corners=False)
+    return so.soft_argmin(torch.squeeze(up, 1)) if dtype == torch.float32 else _sa_ref64(torch.squeeze(up, 1))
+
+
+@pytest.mark.parametrize("shape,size,scale", [((1, 1, 12, 8, 16), (48, 32, 64), 3.0), ((2, 1, 48, 16, 32), (192, 64, 128), 8.0),
+                                               ((1, 1, 5, 7, 9), (20, 28, 36), 1.0), ((1, 1, 6, 5, 7), (17, 13, 23), 5.0),
+                                               ((1, 1, 4, 3, 3), (4, 3, 3), 2.0)])
+def test_upsample_soft_argmin_fwd_bwd(shape, size, scale):
+    torch.manual_seed(30)
+    low = torch.randn(shape) * scale
+    l64 = low.double().requires_grad_(True)
+    ref64 = _upsample_ref(l64, size, torch.float64)
+    g = torch.randn(ref64.shape)
+    ref64.backward(g.double())
+    ref32 = _upsample_ref(low, size)  # torch CPU: the reference's own path
+    lg = gpu(low).requires_grad_(True)
+    out = ops.upsample_soft_argmin(lg, size)
+    out.backward(gpu(g))
+    assert out.shape == ref32.shape
+    mine = float((out.detach().cpu().double() - ref64.detach()).abs().max())
+    theirs = float((ref32.double() - ref64.detach()).abs().max())
+    assert mine <= 1e-4, mine  # the gate, against the exact value (fp32 interpolation noise included)
+    assert float((out.detach().cpu() - ref32).abs().max()) <= 1e-4 + theirs
+    close(lg.grad, l64.grad, rtol=2e-5, floor=2e-5)
+
+
+def test_upsample_soft_argmin_matches_unfused_full_size():
+    """One 544x960 pair: fused kernel vs F.interpolate + this repo's soft-argmin (stock torch
+    interpolate on the GPU as the checker), forward and backward."""
+    torch.manual_seed(31)
+    low = (torch.randn(1, 1, 48, 136, 240, device=DEV) * 6).requires_grad_(True)
+    low2 = low.detach().clone().requires_grad_(True)
+    g = torch.randn(1, 1, 544, 960, device=DEV)
+    out = ops.upsample_soft_argmin(low, (192, 544, 960))
+    up = torch.nn.functional.interpolate(low2, (192, 544, 960), mode="trilinear", align_corners=False)
+    ref = ops.soft_argmin(torch.squeeze(up, 1))
+    # torch's fp32 interpolation and the in-kernel one round the logits differently (~1e-6), which
+    # peaky pixels amplify; both sit within 1e-4 px of the fp64 value
+    ref64 = _sa_ref64(torch.nn.functional.interpolate(low.detach().double(), (192, 544, 960), mode="trilinear",
+                                                        align_corners=False).squeeze(1))
+    assert float((out.detach().double() - ref64).abs().max()) <= 1e-4
+    assert float((out.detach() - ref.detach()).abs().max()) <= 1e-4 + float((ref.detach().double() - ref64).abs().max())
+    out.backward(g)
+    ref.backward(g)
+    close(low.grad, low2.grad, rtol=1e-4, floor=1e-4)  # torch's trilinear backward accumulates with float atomics
+
+
+def test_psmnet_fused_upsample_flag():
+    from activezero_b200.nets.psmnet.psmnet_3 import PSMNet
+
+    torch.manual_seed(1)
+    net = PSMNet(maxdisp=192).cuda().train()
+    a, b = torch.rand(2, 3, 256, 256, device=DEV), torch.rand(2, 3, 256, 256, device=DEV)
+    with torch.no_grad():
+        p_ref = net(a, b)
+        p_ref2 = net(a, b)
+        net.fuse_upsample = True
+        p_fused = net(a, b)
+    assert all(torch.isfinite(p).all() for p in p_fused)
+    for r, r2, f in zip(p_ref, p_ref2, p_fused):  # cuDNN run-to-run noise in the logits is the yardstick
+        assert float((r - f).abs().max()) <= 3.0 * float((r - r2).abs().max()) + 2e-4
