@@ -279,7 +279,7 @@ class ReprojLossFn(torch.autograd.Function):
         B, C, H, W = t.shape
         dev = t.device
         need_bwd = ctx.needs_input_grad[2]
-        warped = torch.empty_like(t) if (want_warped and ps == 1) else None
+        warped = torch.empty_like(t) if want_warped else None
         gpre = torch.empty_like(d) if need_bwd else None
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
         stats = torch.empty((2,), dtype=torch.float64, device=dev)
@@ -309,7 +309,8 @@ class ReprojLossFn(torch.autograd.Function):
 
 
 def reproj_loss(tgt, src, disp, mask=None, ps: int = 1, sign: float = -1.0, want_warped: bool = False):
-    """-> (loss 0-dim, warped [B,C,H,W] or None)."""
+    """-> (loss 0-dim, warped [B,C,H,W] or None).  ``warped`` is the warped image for ps == 1 and
+    the Fold visualisation image of get_reproj_error_patch for ps > 1 (same pass as the loss)."""
     if tgt.requires_grad or src.requires_grad:
         raise ValueError("reproj_loss is differentiable w.r.t. disp only; use warp() for image gradients")
     return ReprojLossFn.apply(tgt, src, disp, _mask_u8(mask, tgt), ps, sign, want_warped)

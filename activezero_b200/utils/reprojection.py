@@ -65,8 +65,8 @@ def get_reprojection_error_old(input_L, input_R, pred_disp_l, mask=None):
 def get_reproj_error_patch(input_L, input_R, pred_disp_l, mask=None, ps=5):
     """reprojection.py:99-127 -- the loss the live trainer uses (ps = 11)."""
     assert ps % 2 == 1
-    loss, _ = ops.reproj_loss(input_L, input_R, pred_disp_l, mask, ps=ps, sign=-1.0, want_warped=False)
-    warped = ops.patch_fold(input_R, pred_disp_l, ps, sign=-1.0) if RETURN_WARPED_PATCH_IMAGE else None
+    loss, warped = ops.reproj_loss(input_L, input_R, pred_disp_l, mask, ps=ps, sign=-1.0,
+                                   want_warped=RETURN_WARPED_PATCH_IMAGE)
     return loss, warped, _int_mask(mask, input_L)
 
 

@@ -156,6 +156,17 @@ def sweep(quick):
         add("reproj_patch_loss_fwd", cfg, time_ms(lambda: ops.reproj_loss(pL, pR, d, mask, ps=PS), flush=True), 4 * 3 * hw + hw)
         add("reproj_patch_loss_fwd+bwd", cfg, time_ms(patch_fb, flush=True), 4 * 3 * hw + hw + 3 * 4 * hw)
         add("patch_fold", cfg, time_ms(lambda: ops.patch_fold(pR, d, PS), flush=True), 4 * 3 * hw)
+        add("reproj_patch_loss+fold_fwd", cfg, time_ms(lambda: ops.reproj_loss(pL, pR, d, mask, ps=PS, want_warped=True),
+                                                       flush=True), 4 * 4 * hw + hw)
+        # the same with a SMOOTH disparity field (what a trained network predicts): the per-pixel random
+        # disparities above make ~half of the shared-memory wavefronts bank conflicts
+        yy, xx = torch.meshgrid(torch.arange(H, device=DEV), torch.arange(W, device=DEV), indexing="ij")
+        ds = (20.0 + 30.0 * torch.sin(xx / 97.0) * torch.cos(yy / 61.0) + 0.013 * xx).view(1, 1, H, W).expand(B, 1, H, W).contiguous()
+        cfg_s = {**cfg, "disp": "smooth"}
+        add("reproj_patch_loss_fwd", cfg_s, time_ms(lambda: ops.reproj_loss(pL, pR, ds, mask, ps=PS), flush=True), 4 * 3 * hw + hw)
+        add("patch_fold", cfg_s, time_ms(lambda: ops.patch_fold(pR, ds, PS), flush=True), 4 * 3 * hw)
+        add("reproj_patch_loss+fold_fwd", cfg_s, time_ms(lambda: ops.reproj_loss(pL, pR, ds, mask, ps=PS, want_warped=True),
+                                                         flush=True), 4 * 4 * hw + hw)
         di = (torch.rand(B, 1, H, W, device=DEV) * 64).int()
         add("scatter_warp", cfg, time_ms(lambda: ops.scatter_warp(d, di, check_sign=False), flush=True), 4 * 3 * hw)
         add("local_contrast_norm", cfg, time_ms(lambda: ops.local_contrast_norm(pL, 9), flush=True), 4 * 3 * hw)

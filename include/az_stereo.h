@@ -98,7 +98,8 @@ int az_warp_bwd(const float* img, const float* disp, const float* lin_x, const f
  *   tgt, src : [B,C,H,W] (tgt = image compared against, src = image that is warped)
  *   disp     : [B,1,H,W];  sign = -1 reproduces apply_disparity(src, -disp), +1 apply_disparity(src, disp)
  *   mask     : [B,1,H,W] uint8 (0/1) or NULL (= all ones)
- *   warped   : [B,C,H,W] or NULL; for ps == 1 the warped image (reprojection.py:89). (ps > 1: use az_patch_fold.)
+ *   warped   : [B,C,H,W] or NULL; for ps == 1 the warped image (reprojection.py:89); for ps > 1 the Fold image of
+ *              reprojection.py:120-125 (what az_patch_fold computes), produced in the same pass as the loss
  *   gpre     : [B,1,H,W] or NULL; m * sum_k (Wu-Lu) * dWu/dxs, consumed by az_reproj_loss_bwd
  *   loss_out : float[1];  stats: double[2] = {sum of squares, sum m} (device), kept for the backward
  *   workspace: az_reproj_workspace_bytes(B,H) bytes, 16-byte aligned
