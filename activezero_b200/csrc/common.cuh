@@ -27,44 +27,6 @@ __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 
-// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) -----------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// global -> shared::cta bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
 // ---- block reductions ---------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -89,6 +51,15 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
         r = warp_sum(r);
     }
     return r;
+}
+
+// 2^x with the MUFU unit only (2 ulp, denormal results flushed to zero).  exp2f() wraps the same
+// instruction in a range fix-up for x < -126 (3 extra instructions per call) that softmax terms
+// below 2^-126 of the maximum do not need.
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // ---- sample position of apply_disparity, in the reference's fp32 op order -----------------

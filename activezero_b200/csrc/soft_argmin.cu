@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_fwd_kernel(const float
 #pragma unroll
             for (int k = 1; k < kChunk; ++k) cm = fmaxf(cm, x[k][j]);
             if (cm > m[j]) {  // rescale the running sums (exp2(-inf) = 0 on the first chunk)
-                const double sc = (double)exp2f((m[j] - cm) * kLog2e);
+                const double sc = (double)fast_ex2((m[j] - cm) * kLog2e);
                 s[j] *= sc;
                 ws[j] *= sc;
                 m[j] = cm;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_fwd_kernel(const float
             const float ref = (m[j] == -INFINITY) ? 0.f : m[j];  // leading -inf planes contribute 0
             float e[kChunk];
 #pragma unroll
-            for (int k = 0; k < kChunk; ++k) e[k] = exp2f((x[k][j] - ref) * kLog2e);
+            for (int k = 0; k < kChunk; ++k) e[k] = fast_ex2((x[k][j] - ref) * kLog2e);
             // tree sums of the chunk in fp32, running sums in fp64
             const float s01 = e[0] + e[1], s23 = e[2] + e[3], s45 = e[4] + e[5], s67 = e[6] + e[7];
             const float w01 = e[1], w23 = fmaf(e[3], 3.f, e[2] * 2.f);
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_bwd_kernel(const float
                 const float dd = (float)(d0 + k);
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    const float p = exp2f(fmaf(x[j] - mx[j], kLog2e, -lb[j]));
+                    const float p = fast_ex2(fmaf(x[j] - mx[j], kLog2e, -lb[j]));
                     r[j] = p * (dd - o[j]) * g[j];
                 }
                 st_stream(reinterpret_cast<VT*>(dst + (int64_t)(d0 + k) * plane), Vec<V>::pack(r));

@@ -24,35 +24,60 @@ __global__ void __launch_bounds__(256) tir_init_kernel(unsigned long long* __res
     }
 }
 
-// grid = (ceil(H*W/256), B)
+template <int V>
+__device__ __forceinline__ void tir_load(const uint8_t* __restrict__ f, double* y) {
+    if (V == 4) {
+        const uchar4 q = *reinterpret_cast<const uchar4*>(f);
+        y[0] = (double)q.x; y[1 % V] = (double)q.y; y[2 % V] = (double)q.z; y[3 % V] = (double)q.w;
+    } else {
+        y[0] = (double)f[0];
+    }
+}
+
+// grid = (ceil(H*W/V/256), B); a thread owns V adjacent pixels (V = 4: one 32-bit load per frame).
+// temporal_ir.py:94-107, numpy float64 op order (no FMA contraction); the frames are read twice (mean,
+// then centred products) -- the second pass hits L1/L2.
+template <int V>
 __global__ void __launch_bounds__(256) tir_slope_kernel(const uint8_t* __restrict__ frames, double* __restrict__ diff,
                                                         unsigned long long* __restrict__ minmax, int T, int64_t HW) {
-    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t p = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V;
     const int b = blockIdx.y;
-    double v = 0.0;
     const bool on = p < HW;
+    const double t_avg = (double)((T - 1) * T / 2) / (double)T;  // np.average of the int ramp
+    double mn = __longlong_as_double(0x7FF0000000000000ll), mx = 0.0;
     if (on) {
         const uint8_t* f = frames + (size_t)b * T * HW + p;
-        // temporal_ir.py:94-107, numpy float64 op order (no FMA contraction)
-        const double t_avg = (double)((T - 1) * T / 2) / (double)T;  // np.average of the int ramp
-        double ysum = 0.0;
-        for (int t = 0; t < T; ++t) ysum += (double)f[(size_t)t * HW];   // exact (integers)
-        const double y_avg = ysum / (double)T;
-        double num = 0.0, den = 0.0;
+        double ysum[V], y[V], num[V], y_avg[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) { ysum[j] = 0.0; num[j] = 0.0; }
+        for (int t = 0; t < T; ++t) {
+            tir_load<V>(f + (size_t)t * HW, y);
+#pragma unroll
+            for (int j = 0; j < V; ++j) ysum[j] += y[j];  // exact (integers)
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) y_avg[j] = ysum[j] / (double)T;
+        double den = 0.0;
         for (int t = 0; t < T; ++t) {
             const double dt = (double)t - t_avg;
-            num = __dadd_rn(num, __dmul_rn((double)f[(size_t)t * HW] - y_avg, dt));
             den = __dadd_rn(den, __dmul_rn(dt, dt));
+            tir_load<V>(f + (size_t)t * HW, y);
+#pragma unroll
+            for (int j = 0; j < V; ++j) num[j] = __dadd_rn(num[j], __dmul_rn(y[j] - y_avg[j], dt));
         }
-        const double slope = num / den;
-        const double icpt = __dsub_rn(y_avg, __dmul_rn(slope, t_avg));
-        const double first = __dadd_rn(__dmul_rn(slope, 0.0), icpt);
-        const double last = __dadd_rn(__dmul_rn(slope, (double)(T - 1)), icpt);
-        v = fabs(__dsub_rn(last, first) / 255.0);   // :110-111
-        diff[(size_t)b * HW + p] = v;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const double slope = num[j] / den;
+            const double icpt = __dsub_rn(y_avg[j], __dmul_rn(slope, t_avg));
+            const double first = __dadd_rn(__dmul_rn(slope, 0.0), icpt);
+            const double last = __dadd_rn(__dmul_rn(slope, (double)(T - 1)), icpt);
+            const double v = fabs(__dsub_rn(last, first) / 255.0);  // :110-111
+            diff[(size_t)b * HW + p + j] = v;
+            mn = fmin(mn, v);
+            mx = fmax(mx, v);
+        }
     }
     // block min / max, then one integer atomic each
-    double mn = on ? v : __longlong_as_double(0x7FF0000000000000ll), mx = on ? v : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -174,8 +199,13 @@ extern "C" int az_temporal_ir(const uint8_t* frames, float* pattern, void* works
     const int64_t HW = H * W;
     tir_init_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(minmax, (int)B);
     AZ_LAUNCH_CHECK();
-    dim3 g1((unsigned)ceil_div(HW, 256), (unsigned)B);
-    tir_slope_kernel<<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
+    if (HW % 4 == 0 && (reinterpret_cast<uintptr_t>(frames) & 3u) == 0) {
+        dim3 g1((unsigned)ceil_div(HW / 4, 256), (unsigned)B);
+        tir_slope_kernel<4><<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
+    } else {
+        dim3 g1((unsigned)ceil_div(HW, 256), (unsigned)B);
+        tir_slope_kernel<1><<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
+    }
     AZ_LAUNCH_CHECK();
     const int TW = kTirTX + (int)ks - 1, TH = kTirTY + (int)ks - 1;
     const size_t smem = ((size_t)TW * TH + (size_t)TH * kTirTX) * sizeof(double);

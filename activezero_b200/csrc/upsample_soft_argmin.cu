@@ -116,14 +116,14 @@ __global__ void __launch_bounds__(kUTW * kUTH) upsample_soft_argmin_fwd_kernel(
             const float lf = fmaf(l1[db], diff, va), ll = fmaf(l1[de - 1], diff, va);
             const float cm = fmaxf(lf, ll);
             if (cm > m) {
-                const double sc = (double)exp2f((m - cm) * kLog2eU);
+                const double sc = (double)fast_ex2((m - cm) * kLog2eU);
                 s *= sc;
                 ws *= sc;
                 m = cm;
             }
             float cs = 0.f, cw = 0.f, kf = 0.f;
             for (int d = db; d < de; ++d) {
-                const float e = exp2f((fmaf(l1[d], diff, va) - m) * kLog2eU);
+                const float e = fast_ex2((fmaf(l1[d], diff, va) - m) * kLog2eU);
                 cs += e;
                 cw = fmaf(kf, e, cw);
                 kf += 1.0f;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kUTW * kUTH) upsample_soft_argmin_bwd_pix_kern
         float ga = 0.f, gb = 0.f, df = (float)db;
         for (int d = db; d < de; ++d) {
             const float w1 = l1[d];
-            const float p = exp2f(fmaf(fmaf(w1, diff, va) - m, kLog2eU, -l2s));
+            const float p = fast_ex2(fmaf(fmaf(w1, diff, va) - m, kLog2eU, -l2s));
             const float gc = p * (df - out) * g;
             gb = fmaf(w1, gc, gb);
             ga += gc;
@@ -244,6 +244,9 @@ __global__ void __launch_bounds__(kUTW * kUTH) upsample4_soft_argmin_fwd_kernel(
     float va = bil(tile, t);
     float m = va;                  // d = 0, 1 sample plane 0 exactly
     double s = 2.0, ws = 1.0;      // e = 1 at d = 0 and d = 1
+    // interval sums are collected in fp32 and flushed to the fp64 running sums every 8 intervals (and
+    // before a rescale): conversions share the MUFU/XU pipe with the 192 ex2 per pixel that bound this kernel
+    float fs = 0.f, fw = 0.f;
     const float* pl = tile;
     for (int q = 0; q + 1 < Dq; ++q) {
         pl += FHW;
@@ -252,28 +255,36 @@ __global__ void __launch_bounds__(kUTW * kUTH) upsample4_soft_argmin_fwd_kernel(
         const float l0 = fmaf(0.125f, diff, va), l1 = fmaf(0.375f, diff, va);
         const float l2 = fmaf(0.625f, diff, va), l3 = fmaf(0.875f, diff, va);
         const float cm = fmaxf(l0, l3);
-        if (cm > m) {
-            const double sc = (double)exp2f((m - cm) * kLog2eU);
-            s *= sc;
-            ws *= sc;
-            m = cm;
+        if (cm > m || (q & 7) == 7) {
+            s += (double)fs;
+            ws += (double)fw;
+            fs = 0.f;
+            fw = 0.f;
+            if (cm > m) {
+                const double sc = (double)fast_ex2((m - cm) * kLog2eU);
+                s *= sc;
+                ws *= sc;
+                m = cm;
+            }
         }
-        const float e0 = exp2f((l0 - m) * kLog2eU), e1 = exp2f((l1 - m) * kLog2eU);
-        const float e2 = exp2f((l2 - m) * kLog2eU), e3 = exp2f((l3 - m) * kLog2eU);
+        const float e0 = fast_ex2((l0 - m) * kLog2eU), e1 = fast_ex2((l1 - m) * kLog2eU);
+        const float e2 = fast_ex2((l2 - m) * kLog2eU), e3 = fast_ex2((l3 - m) * kLog2eU);
         const float es = (e0 + e1) + (e2 + e3);
         const float ew = fmaf(3.0f, e3, fmaf(2.0f, e2, e1));
-        s += (double)es;
-        ws += fma((double)(4 * q + 2), (double)es, (double)ew);
+        fs += es;
+        fw += fmaf((float)(4 * q + 2), es, ew);
         va = vb;
     }
+    s += (double)fs;
+    ws += (double)fw;
     {   // d = D-2, D-1 sample plane Dq-1 exactly
         if (va > m) {
-            const double sc = (double)exp2f((m - va) * kLog2eU);
+            const double sc = (double)fast_ex2((m - va) * kLog2eU);
             s *= sc;
             ws *= sc;
             m = va;
         }
-        const double e = (double)exp2f((va - m) * kLog2eU);
+        const double e = (double)fast_ex2((va - m) * kLog2eU);
         s += 2.0 * e;
         ws += e * (double)(2 * D - 3);
     }
@@ -307,7 +318,7 @@ __global__ void __launch_bounds__(kUTW * kUTH) upsample4_soft_argmin_bwd_pix_ker
     // d = 0, 1 -> plane 0 with weight 1
     float carry;
     {
-        const float p = exp2f(fmaf(va - m, kLog2eU, -l2s));
+        const float p = fast_ex2(fmaf(va - m, kLog2eU, -l2s));
         carry = p * g * ((0.0f - out) + (1.0f - out));
     }
     const float* pl = tile;
@@ -316,10 +327,10 @@ __global__ void __launch_bounds__(kUTW * kUTH) upsample4_soft_argmin_bwd_pix_ker
         const float vb = bil(pl, t);
         const float diff = vb - va;
         const float bo = (float)(4 * q + 2) - out;
-        const float p0 = exp2f(fmaf(fmaf(0.125f, diff, va) - m, kLog2eU, -l2s));
-        const float p1 = exp2f(fmaf(fmaf(0.375f, diff, va) - m, kLog2eU, -l2s));
-        const float p2 = exp2f(fmaf(fmaf(0.625f, diff, va) - m, kLog2eU, -l2s));
-        const float p3 = exp2f(fmaf(fmaf(0.875f, diff, va) - m, kLog2eU, -l2s));
+        const float p0 = fast_ex2(fmaf(fmaf(0.125f, diff, va) - m, kLog2eU, -l2s));
+        const float p1 = fast_ex2(fmaf(fmaf(0.375f, diff, va) - m, kLog2eU, -l2s));
+        const float p2 = fast_ex2(fmaf(fmaf(0.625f, diff, va) - m, kLog2eU, -l2s));
+        const float p3 = fast_ex2(fmaf(fmaf(0.875f, diff, va) - m, kLog2eU, -l2s));
         const float g0 = p0 * (bo * g), g1 = p1 * ((bo + 1.0f) * g);
         const float g2 = p2 * ((bo + 2.0f) * g), g3 = p3 * ((bo + 3.0f) * g);
         const float gb = fmaf(0.875f, g3, fmaf(0.625f, g2, fmaf(0.375f, g1, 0.125f * g0)));
@@ -329,33 +340,53 @@ __global__ void __launch_bounds__(kUTW * kUTH) upsample4_soft_argmin_bwd_pix_ker
         va = vb;
     }
     {   // d = D-2, D-1 -> plane Dq-1 with weight 1
-        const float p = exp2f(fmaf(va - m, kLog2eU, -l2s));
+        const float p = fast_ex2(fmaf(va - m, kLog2eU, -l2s));
         Gp[(size_t)(Dq - 1) * HW] = carry + p * g * (((float)(D - 2) - out) + ((float)(D - 1) - out));
     }
 }
 
-// backward stage 2: T[b,q,y,w] = sum_x wx(x,w) * G[b,q,y,x].   grid = (ceil(Wq/128), H, B*Dq)
+// backward stage 2: T[b,q,y,w] = sum_x wx(x,w) * G[b,q,y,x].
+// The tap weights of a low-res column depend on w only: each thread computes its <= kMaxTaps weights once
+// and applies them to kRowsPerCta rows.  grid = (ceil(Wq/128), ceil(H/kRowsPerCta), B*Dq)
+constexpr int kMaxTaps = 16, kRowsPerCta = 8;
+
+__device__ __forceinline__ void tap_range(float scale, int w, int out_size, int& lo, int& hi) {
+    const float inv = 1.0f / scale;  // output indices whose source index can touch w: src in (w-1, w+1)
+    lo = max((int)floorf(((float)w - 1.0f + 0.5f) * inv - 0.5f) - 1, 0);
+    hi = min((int)ceilf(((float)w + 1.0f + 0.5f) * inv - 0.5f) + 1, out_size - 1);
+}
+
+__device__ __forceinline__ float tap_weight(float scale, int x, int w, int in_size) {
+    const Lerp l = src_index(scale, x, in_size);
+    float wt = 0.f;
+    if (l.i0 == w) wt += l.l0;
+    if (l.i1 == w) wt += l.l1;
+    return wt;
+}
+
 __global__ void __launch_bounds__(128) upsample_bwd_reduce_x_kernel(const float* __restrict__ G, float* __restrict__ T,
                                                                    int H, int W, int Wq, float sw) {
     const int w = blockIdx.x * 128 + threadIdx.x;
     if (w >= Wq) return;
-    const size_t row = (size_t)blockIdx.z * H + blockIdx.y;
-    const float* g = G + row * W;
-    // output columns whose source index can touch w: src(x) in (w-1, w+1)
-    const float inv = 1.0f / sw;
-    int xlo = (int)floorf(((float)w - 1.0f + 0.5f) * inv - 0.5f) - 1;
-    int xhi = (int)ceilf(((float)w + 1.0f + 0.5f) * inv - 0.5f) + 1;
-    xlo = max(xlo, 0);
-    xhi = min(xhi, W - 1);
-    float acc = 0.f;
-    for (int x = xlo; x <= xhi; ++x) {
-        const Lerp l = src_index(sw, x, Wq);
-        float wt = 0.f;
-        if (l.i0 == w) wt += l.l0;
-        if (l.i1 == w) wt += l.l1;
-        if (wt != 0.f) acc = fmaf(wt, __ldg(g + x), acc);
+    int xlo, xhi;
+    tap_range(sw, w, W, xlo, xhi);
+    // drop zero-weight taps at both ends so that the window fits kMaxTaps (the host checks the bound)
+    while (xlo < xhi && tap_weight(sw, xlo, w, Wq) == 0.f) ++xlo;
+    while (xhi > xlo && tap_weight(sw, xhi, w, Wq) == 0.f) --xhi;
+    float wt[kMaxTaps];
+#pragma unroll
+    for (int t = 0; t < kMaxTaps; ++t) wt[t] = (xlo + t <= xhi) ? tap_weight(sw, xlo + t, w, Wq) : 0.f;
+    const int y0 = blockIdx.y * kRowsPerCta;
+    const int y1 = min(y0 + kRowsPerCta, H);
+    for (int y = y0; y < y1; ++y) {
+        const size_t row = (size_t)blockIdx.z * H + y;
+        const float* g = G + row * W + xlo;
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < kMaxTaps; ++t)
+            if (xlo + t <= xhi) acc = fmaf(wt[t], __ldg(g + t), acc);
+        T[row * Wq + w] = acc;
     }
-    T[row * Wq + w] = acc;
 }
 
 // backward stage 3: glow[b,q,h,w] = sum_y wy(y,h) * T[b,q,y,w].   grid = (ceil(Wq/128), Hq, B*Dq)
@@ -460,7 +491,8 @@ extern "C" int az_upsample_soft_argmin_bwd(const float* lowres, const float* dis
             B * H * W);
     }
     AZ_LAUNCH_CHECK();
-    dim3 gx((unsigned)ceil_div(Wq, 128), (unsigned)H, (unsigned)(B * Dq));
+    if (2.0 * (double)W / (double)Wq + 3.0 > kMaxTaps) return AZ_ERR_BAD_ARG;  // horizontal upsampling factor <= 6
+    dim3 gx((unsigned)ceil_div(Wq, 128), (unsigned)ceil_div(H, kRowsPerCta), (unsigned)(B * Dq));
     upsample_bwd_reduce_x_kernel<<<gx, 128, 0, st>>>(G, T, (int)H, (int)W, (int)Wq, sw);
     AZ_LAUNCH_CHECK();
     dim3 gy((unsigned)ceil_div(Wq, 128), (unsigned)Hq, (unsigned)(B * Dq));
