@@ -51,6 +51,9 @@ ALGO_BYTES = {
 }
 
 
+BOUND = {"concat_volume_fwd": "hbm", "soft_argmin_fwd": "hbm", "reproj_patch_loss+fold_fwd": "shared-memory latency/issue"}
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -288,7 +291,42 @@ def run_b200(args, rank, world, local_rank):
         ms_e2e = s2.elapsed_time(e2)
         loss_val = float(res_loss)
 
-    ms_total, ms_e2e = dist_util.max_over_ranks([ms_total, ms_e2e], dev)
+        # ---- informational variant: the same step when the soft-argmin is fed by the
+        # LOW-RESOLUTION logits and fused with the trilinear upsample, i.e. the [B,192,544,960] tensor is
+        # never materialised (nor shipped over PCIe).  Not part of `value` / `e2e`.
+        low_host = (torch.randn(n_pairs, 1, DQ, HQ, WQ, generator=torch.Generator().manual_seed(7 + first_pair)) * 4.0).pin_memory()
+        low_dev = low_host.to(dev)
+
+        def fused_step(Ld, Rd, lowd, pLd, pRd, md):
+            vol = ops.build_concat_volume(Ld, Rd, DQ)
+            disp = ops.upsample_soft_argmin(lowd, (D, H, W))
+            loss, vis = ops.reproj_loss(pLd, pRd, disp, md, ps=PS, sign=-1.0, want_warped=True)
+            return vol, disp, loss, vis
+
+        def fused_e2e_step():
+            dv = [host[0].to(dev, non_blocking=True), host[1].to(dev, non_blocking=True),
+                  low_host.to(dev, non_blocking=True)] + [t.to(dev, non_blocking=True) for t in host[3:]]
+            _, disp, loss, _ = fused_step(*dv)
+            res_disp.copy_(disp, non_blocking=True)
+            res_loss.copy_(loss, non_blocking=True)
+
+        for _ in range(3):
+            fused_step(L, R, low_dev, pat_L, pat_R, mask)
+            fused_e2e_step()
+        f0, f1, f2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        barrier()
+        f0.record()
+        for _ in range(args.steps):
+            fused_step(L, R, low_dev, pat_L, pat_R, mask)
+        f1.record()
+        for _ in range(e2e_steps):
+            fused_e2e_step()
+        f2.record()
+        barrier()
+        ms_fused, ms_fused_e2e = f0.elapsed_time(f1), f1.elapsed_time(f2)
+        h2d_fused = h2d - host[2].numel() * 4 + low_host.numel() * 4
+
+    ms_total, ms_e2e, ms_fused, ms_fused_e2e = dist_util.max_over_ranks([ms_total, ms_e2e, ms_fused, ms_fused_e2e], dev)
 
     if rank == 0:
         per_kernel = {}
@@ -301,8 +339,11 @@ def run_b200(args, rank, world, local_rank):
             gbs = ALGO_BYTES[n] / (per_kernel[n] * 1e-3) / 1e9
             kernels.append({"kernel": n, "ms": per_kernel[n], "algo_bytes": ALGO_BYTES[n], "achieved_gbs": gbs,
                             "frac": gbs / peak, "share": per_kernel[n] / sum(per_kernel.values()),
-                            "traffic": traffic.get(n)})
-        dom = max(kernels, key=lambda k: k["ms"])
+                            "traffic": traffic.get(n), "bound": BOUND[n]})
+        # the roofline object is an HBM roofline: it describes the slowest of the HBM-bound kernels; the
+        # patch kernel (121 taps per pixel out of shared memory, ~9 MB of compulsory traffic per pair) is
+        # listed with its share in `kernels` and cannot be placed on a bandwidth roofline meaningfully
+        dom = max((k for k in kernels if k["bound"] == "hbm"), key=lambda k: k["ms"])
         line = {
             "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -316,8 +357,15 @@ def run_b200(args, rank, world, local_rank):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak,
                          "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
+                         "selection": "slowest HBM-bound kernel of the step (see kernels[] for all shares)",
+                         "hbm_bound_share_of_step": sum(k["share"] for k in kernels if k["bound"] == "hbm"),
                          "pipeline_frac": sum(ALGO_BYTES.values()) / (ms_total / args.steps * 1e-3) / 1e9 / peak},
             "kernels": kernels,
+            "variant_fused_upsample": {
+                "note": "informational, SURVEY §8f-1: soft-argmin fused with the trilinear upsample reads the "
+                        "[B,1,48,136,240] low-res logits; not the BASELINE config, not part of value/e2e",
+                "value": world * B * args.steps / (ms_fused * 1e-3), "ms_per_step": ms_fused / args.steps,
+                "e2e_value": world * B * e2e_steps / (ms_fused_e2e * 1e-3), "h2d_bytes_per_step": h2d_fused, "unit": UNIT},
             "loss_check": loss_val,
         }
         if world == 1 and not args.no_cpu_baseline:
