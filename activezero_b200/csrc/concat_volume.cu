@@ -248,13 +248,10 @@ extern "C" int az_concat_volume_fwd(const float* L, const float* R, float* vol, 
         const int rows_cap = (P + W4 - 1) / W4 + 1;
         const size_t smem = (size_t)4 * rows_cap * (pad + W) * sizeof(float);
         if (smem <= 200 * 1024) {
-            static bool attr_done = false;
-            if (!attr_done) {
-                cudaError_t e = cudaFuncSetAttribute(concat_fwd_vec4_kernel,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-                if (e != cudaSuccess) return (int)e;
-                attr_done = true;
-            }
+            // per launch, not cached: the attribute is per device and the call costs ~1 us
+            cudaError_t e = cudaFuncSetAttribute(concat_fwd_vec4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 200 * 1024);
+            if (e != cudaSuccess) return (int)e;
             dim3 grid((unsigned)ceil_div(H * W4, P), (unsigned)(2 * C), (unsigned)B);
             concat_fwd_vec4_kernel<<<grid, kFwdThreads, smem, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq, pad,
                                                                    rows_cap);
