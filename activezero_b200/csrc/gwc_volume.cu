@@ -131,7 +131,7 @@ __device__ __forceinline__ void fma4(float4& acc, const float4& u, const float4&
 // smem: Ls[CPT][rows_cap][W + tail] (zero tail) | Rs[CPT][rows_cap][pad + W] (zero prefix)
 // ------------------------------------------------------------------------------------------
 template <int CPG, int CPT>
-__global__ void __launch_bounds__(kGwcThreads, 2) gwc_bwd_direct_kernel(const float* __restrict__ gvol,
+__global__ void __launch_bounds__(kGwcThreads, 3) gwc_bwd_direct_kernel(const float* __restrict__ gvol,
                                                                        const float* __restrict__ L,
                                                                        const float* __restrict__ R,
                                                                        float* __restrict__ gL, float* __restrict__ gR,

@@ -379,3 +379,29 @@ def local_contrast_norm(image, kernel_size: int = 9, eps: float = 1e-5):
         _lib.call("az_local_contrast_norm", _ptr(im), _ptr(normed), _ptr(std), B, Cin, H, W, int(kernel_size),
                   float(eps), _stream())
     return normed, std
+
+
+def error_metric_sums(disp_gt, depth_gt, disp_pred, mask, depth_pred=None, focal_length=None, baseline=None):
+    """The eight masked sums behind compute_err_metric (utils/cascade_metrics.py:16-57) as ONE
+    float64[8] device tensor: n, sum|ddisp|, #>1, #>2, sum clip(|dz*1000|,0,100), #dz>2mm, #>4mm, #>8mm."""
+    dg = _cuda_f32(disp_gt.detach(), "disp_gt")
+    zg = _cuda_f32(depth_gt.detach(), "depth_gt")
+    dp = _cuda_f32(disp_pred.detach(), "disp_pred")
+    if dg.dim() != 4 or dg.shape[1] != 1 or zg.shape != dg.shape or dp.shape != dg.shape:
+        raise ValueError("error metrics: disp_gt, depth_gt, disp_pred must all be [B,1,H,W]")
+    B, _, H, W = dg.shape
+    m = _mask_u8(mask, dg)
+    zp = f = bl = None
+    if depth_pred is not None:
+        zp = _cuda_f32(depth_pred.detach(), "depth_pred")
+    else:
+        f = _cuda_f32(focal_length.detach().reshape(-1), "focal_length")
+        bl = _cuda_f32(baseline.detach().reshape(-1), "baseline")
+        if f.numel() != B or bl.numel() != B:
+            raise ValueError("error metrics: focal_length and baseline must hold one value per sample")
+    out = torch.empty((8,), dtype=torch.float64, device=dg.device)
+    ws = torch.empty((_lib.query("az_error_metrics_workspace_bytes", B, H, W),), dtype=torch.uint8, device=dg.device)
+    with torch.cuda.device(dg.device):
+        _lib.call("az_error_metrics", _ptr(dg), _ptr(zg), _ptr(dp), _ptr(zp), _ptr(f), _ptr(bl), _ptr(m), _ptr(out),
+                  _ptr(ws), B, H, W, _stream())
+    return out

@@ -139,6 +139,18 @@ int az_temporal_ir(const uint8_t* frames, float* pattern, void* workspace,
 int az_local_contrast_norm(const float* image, float* normed, float* std, int64_t B, int64_t Cin,
                            int64_t H, int64_t W, int64_t ks, float eps, void* stream);
 
+/* ---- fused error metrics -- utils/cascade_metrics.py:16-57 (compute_err_metric) ----
+ * One pass + one 64-byte read instead of seven boolean gathers with .item() syncs.
+ * disp_gt, depth_gt, disp_pred: [B,1,H,W]; depth_pred: [B,1,H,W] or NULL (then focal_length*baseline/disp_pred
+ * with focal_length, baseline: float[B]); mask: [B,1,H,W] uint8.
+ * out: double[8] (device) = { n, sum|ddisp|, #(|ddisp|>1), #(|ddisp|>2), sum clip(|dz*1000|,0,100),
+ *                             #(|dz|>2e-3), #(|dz|>4e-3), #(|dz|>8e-3) };
+ * workspace: az_error_metrics_workspace_bytes(B,H,W) bytes. */
+int64_t az_error_metrics_workspace_bytes(int64_t B, int64_t H, int64_t W);
+int az_error_metrics(const float* disp_gt, const float* depth_gt, const float* disp_pred, const float* depth_pred,
+                     const float* focal_length, const float* baseline, const uint8_t* mask, double* out,
+                     void* workspace, int64_t B, int64_t H, int64_t W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -255,6 +255,35 @@ def gen_temporal_ir():
     )
 
 
+def gen_err_metrics():
+    """utils/cascade_metrics.py:compute_err_metric called directly (train.py:348-351 shapes:
+    focal_length / baseline are [bs,1,1,1])."""
+    ref_loader.load()
+    sys.path.insert(0, ref_loader.REFERENCE_ROOT)
+    try:
+        cm = importlib.import_module("utils.cascade_metrics")
+    finally:
+        sys.path.remove(ref_loader.REFERENCE_ROOT)
+    torch.manual_seed(9)
+    B, H, W = 2, 20, 36
+    disp_gt = torch.rand(B, 1, H, W) * 80 + 1
+    disp_pred = disp_gt + torch.randn(B, 1, H, W) * 1.5
+    focal = torch.tensor([[[[430.0]]], [[[455.5]]]])
+    base = torch.tensor([[[[0.055]]], [[[0.0545]]]])
+    depth_gt = focal * base / disp_gt + torch.randn(B, 1, H, W) * 1e-3
+    mask = torch.rand(B, 1, H, W) > 0.3
+    m1 = cm.compute_err_metric(disp_gt, depth_gt, disp_pred, focal, base, mask)
+    depth_pred = focal * base / disp_pred + 2e-3
+    m2 = cm.compute_err_metric(disp_gt, depth_gt, disp_pred, focal, base, mask, depth_pred=depth_pred)
+    out = dict(disp_gt=_np(disp_gt), disp_pred=_np(disp_pred), depth_gt=_np(depth_gt), focal=_np(focal), base=_np(base),
+               mask=_np(mask), depth_pred=_np(depth_pred))
+    for k, v in m1.items():
+        out["m1_" + k] = np.float64(v)
+    for k, v in m2.items():
+        out["m2_" + k] = np.float64(v)
+    np.savez_compressed(os.path.join(GOLDEN, "err_metrics.npz"), **out)
+
+
 def gen_state_dict_keys():
     """Names and shapes of every state_dict entry of both reference PSMNet variants
     (checkpoint compatibility contract, test.py:341-342 / train.py:155-170)."""
@@ -280,7 +309,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     for fn in (gen_scatter_warp, gen_temporal_ir, gen_reprojection, gen_soft_argmin, gen_psmnet_inline,
-               gen_state_dict_keys):
+               gen_state_dict_keys, gen_err_metrics):
         print("generating", fn.__name__, flush=True)
         fn()
     for f in sorted(os.listdir(GOLDEN)):

@@ -312,6 +312,32 @@ def temporal_ir_pattern(frames: np.ndarray, ks: int = 11, threshold: float = 0.0
 
 
 # ----------------------------------------------------------------------------
+# §8f rank 4  error metrics            utils/cascade_metrics.py:16-57
+# ----------------------------------------------------------------------------
+
+def compute_err_metric(disp_gt, depth_gt, disp_pred, focal_length, baseline, mask, depth_pred=None):
+    """cascade_metrics.py:30-57: masked EPE (:30), |diff| > 1 / 2 px rates (:31-33), depth from
+    disparity (:36-37), mean |dz| in mm clipped to 100 (:39-42), 2/4/8 mm outlier rates (:45-48)."""
+    with torch.no_grad():
+        sel_gt, sel_pred = disp_gt[mask], disp_pred[mask]
+        adiff = torch.abs(sel_gt - sel_pred)
+        n = adiff.numel()
+        if depth_pred is None:
+            depth_pred = focal_length * baseline / disp_pred
+        mm = torch.clip(torch.abs(depth_gt[mask] * 1000 - depth_pred[mask] * 1000), min=0, max=100)
+        dz = torch.abs(depth_gt[mask] - depth_pred[mask])
+        return {
+            "epe": F.l1_loss(sel_pred, sel_gt, reduction="mean").item(),
+            "bad1": int((adiff > 1).sum()) / n,
+            "bad2": int((adiff > 2).sum()) / n,
+            "depth_abs_err": torch.mean(mm).item(),
+            "depth_err2": int((dz > 2e-3).sum()) / dz.numel(),
+            "depth_err4": int((dz > 4e-3).sum()) / dz.numel(),
+            "depth_err8": int((dz > 8e-3).sum()) / dz.numel(),
+        }
+
+
+# ----------------------------------------------------------------------------
 # Closed forms (derived from the lines above; used to check kernel formulas on
 # tiny shapes in float64 -- SURVEY.md §8a "closed forms certified")
 # ----------------------------------------------------------------------------

@@ -604,3 +604,38 @@ def test_psmnet_fused_upsample_flag():
     assert all(torch.isfinite(p).all() for p in p_fused)
     for r, r2, f in zip(p_ref, p_ref2, p_fused):  # cuDNN run-to-run noise in the logits is the yardstick
         assert float((r - f).abs().max()) <= 3.0 * float((r - r2).abs().max()) + 2e-4
+
+
+# --------------------------------------------------------------------------- §8f-4 fused error metrics
+def test_err_metrics_golden_and_random(golden):
+    from activezero_b200.utils.cascade_metrics import compute_err_metric
+
+    g = golden("err_metrics")
+    args = [gpu(T(g[k])) for k in ("disp_gt", "depth_gt", "disp_pred", "focal", "base", "mask")]
+    m1 = compute_err_metric(*args)
+    m2 = compute_err_metric(*args, depth_pred=gpu(T(g["depth_pred"])))
+    for tag, m in (("m1_", m1), ("m2_", m2)):
+        assert set(m) == {"epe", "bad1", "bad2", "depth_abs_err", "depth_err2", "depth_err4", "depth_err8"}
+        for k, v in m.items():
+            assert isinstance(v, float)
+            if k in ("epe", "depth_abs_err"):
+                np.testing.assert_allclose(v, float(g[tag + k]), rtol=1e-6)
+            else:
+                assert v == float(g[tag + k]), k  # counts are exact
+    torch.manual_seed(40)
+    B, H, W = 8, 544, 960
+    disp_gt = torch.rand(B, 1, H, W) * 100 + 1
+    disp_pred = disp_gt + torch.randn(B, 1, H, W) * 2
+    focal, base = torch.rand(B, 1, 1, 1) * 50 + 400, torch.rand(B, 1, 1, 1) * 0.01 + 0.05
+    depth_gt = focal * base / disp_gt + torch.randn(B, 1, H, W) * 2e-3
+    mask = torch.rand(B, 1, H, W) > 0.4
+    ref = so.compute_err_metric(disp_gt, depth_gt, disp_pred, focal, base, mask)
+    out = compute_err_metric(gpu(disp_gt), gpu(depth_gt), gpu(disp_pred), gpu(focal), gpu(base), gpu(mask))
+    for k in ref:
+        if k in ("epe", "depth_abs_err"):
+            np.testing.assert_allclose(out[k], ref[k], rtol=1e-5)
+        else:
+            assert out[k] == ref[k], k
+    empty = compute_err_metric(gpu(disp_gt), gpu(depth_gt), gpu(disp_pred), gpu(focal), gpu(base),
+                               torch.zeros_like(mask).to(DEV))
+    assert all(np.isnan(v) for v in empty.values())

@@ -200,3 +200,14 @@ def test_c_restatement(tmp_path, golden):
     out = np.empty((B, 1, H, W), np.float64)
     lib.azo_soft_argmin_f64(vp(out.ctypes.data), vp(logits.ctypes.data), B, D, H, W)
     assert np.abs(out - g["pred"]).max() <= 1e-4
+
+
+def test_err_metrics(golden):
+    """§8f rank 4: the restatement of compute_err_metric against the real function."""
+    g = golden("err_metrics")
+    args = [T(g[k]) for k in ("disp_gt", "depth_gt", "disp_pred", "focal", "base", "mask")]
+    m1 = so.compute_err_metric(*args)
+    m2 = so.compute_err_metric(*args, depth_pred=T(g["depth_pred"]))
+    for tag, m in (("m1_", m1), ("m2_", m2)):
+        for k, v in m.items():
+            np.testing.assert_allclose(v, float(g[tag + k]), rtol=1e-7)
