@@ -15,6 +15,11 @@ from typing import Optional
 import torch
 from torch.autograd.function import once_differentiable
 
+# Under torch.autocast the operators still compute in fp32 (the reference's PSMNet path does not use AMP;
+# the decorators only make the Functions safe to call from an autocast region).
+_fwd32 = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_bwd = torch.amp.custom_bwd(device_type="cuda")
+
 from . import _lib
 
 _NULL = ctypes.c_void_p(0)
@@ -59,6 +64,7 @@ class ConcatVolumeFn(torch.autograd.Function):
     """nets/psmnet/psmnet.py:151-165 and its autograd."""
 
     @staticmethod
+    @_fwd32
     def forward(ctx, ref_feat, tgt_feat, num_disp: int):
         L = _cuda_f32(ref_feat, "ref_feat")
         R = _cuda_f32(tgt_feat, "tgt_feat")
@@ -73,6 +79,7 @@ class ConcatVolumeFn(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_bwd
     def backward(ctx, gvol):
         B, C, H, W, Dq = ctx.dims
         g = _cuda_f32(gvol, "grad_volume")
@@ -93,6 +100,7 @@ def build_concat_volume(ref_feat, tgt_feat, num_disp: int):
 # ----------------------------------------------------------------------------
 class GwcVolumeFn(torch.autograd.Function):
     @staticmethod
+    @_fwd32
     def forward(ctx, ref_feat, tgt_feat, num_disp: int, num_groups: int):
         L = _cuda_f32(ref_feat, "ref_feat")
         R = _cuda_f32(tgt_feat, "tgt_feat")
@@ -111,6 +119,7 @@ class GwcVolumeFn(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_bwd
     def backward(ctx, gvol):
         L, R = ctx.saved_tensors
         B, C, H, W, Dq, G = ctx.dims
@@ -134,6 +143,7 @@ class SoftArgminFn(torch.autograd.Function):
     psmnet_submodule.py:80-89) fused; takes LOGITS."""
 
     @staticmethod
+    @_fwd32
     def forward(ctx, cost):
         c = _cuda_f32(cost, "cost")
         if c.dim() != 4:
@@ -150,6 +160,7 @@ class SoftArgminFn(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_bwd
     def backward(ctx, gdisp):
         c, disp, lse = ctx.saved_tensors
         B, D, H, W = c.shape
@@ -171,6 +182,7 @@ class UpsampleSoftArgminFn(torch.autograd.Function):
     low-resolution logits only."""
 
     @staticmethod
+    @_fwd32
     def forward(ctx, lowres, out_size):
         c = _cuda_f32(lowres, "lowres")
         if c.dim() == 5:
@@ -192,6 +204,7 @@ class UpsampleSoftArgminFn(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_bwd
     def backward(ctx, gdisp):
         c, disp, stats = ctx.saved_tensors
         B, Dq, Hq, Wq, D, H, W = ctx.dims
@@ -217,6 +230,7 @@ class WarpFn(torch.autograd.Function):
     """apply_disparity (utils/reprojection.py:13-35)."""
 
     @staticmethod
+    @_fwd32
     def forward(ctx, img, disp):
         im = _cuda_f32(img, "img")
         d = _cuda_f32(disp, "disp")
@@ -232,6 +246,7 @@ class WarpFn(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_bwd
     def backward(ctx, gout):
         im, d = ctx.saved_tensors
         B, C, H, W = im.shape
@@ -270,6 +285,7 @@ class ReprojLossFn(torch.autograd.Function):
     w.r.t. ``disp`` only (what the trainer needs: the images are data)."""
 
     @staticmethod
+    @_fwd32
     def forward(ctx, tgt, src, disp, mask_u8, ps: int, sign: float, want_warped: bool):
         t = _cuda_f32(tgt, "tgt")
         s = _cuda_f32(src, "src")
@@ -297,6 +313,7 @@ class ReprojLossFn(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @_bwd
     def backward(ctx, gloss, _gwarped):
         gpre, stats = ctx.saved_tensors
         B, C, H, W, ps, sign = ctx.meta

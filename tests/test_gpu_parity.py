@@ -639,3 +639,21 @@ def test_err_metrics_golden_and_random(golden):
     empty = compute_err_metric(gpu(disp_gt), gpu(depth_gt), gpu(disp_pred), gpu(focal), gpu(base),
                                torch.zeros_like(mask).to(DEV))
     assert all(np.isnan(v) for v in empty.values())
+
+
+def test_ops_inside_autocast_compute_in_fp32():
+    torch.manual_seed(50)
+    cost = torch.randn(1, 48, 8, 16, device=DEV, requires_grad=True)
+    L = torch.randn(1, 8, 6, 16, device=DEV, requires_grad=True)
+    R = torch.randn(1, 8, 6, 16, device=DEV)
+    ref = ops.soft_argmin(cost)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = ops.soft_argmin(cost.to(torch.bfloat16).float() * 0 + cost)  # fp32 stays fp32
+        half_in = ops.soft_argmin(cost.half())                              # half input is cast up, not rejected
+        vol = ops.build_concat_volume(L, R, 4)
+    assert out.dtype == torch.float32 and torch.equal(out, ref)
+    assert half_in.dtype == torch.float32
+    assert float((half_in - ops.soft_argmin(cost.half().float())).abs().max()) == 0.0
+    assert vol.dtype == torch.float32 and torch.equal(vol, so.concat_volume(L.detach(), R, 4))
+    (out.sum() + vol.sum()).backward()
+    assert cost.grad is not None and L.grad is not None and cost.grad.dtype == torch.float32
