@@ -46,13 +46,15 @@ SIGNATURES = {
     "az_scatter_warp": (ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "az_temporal_ir_workspace_bytes": (_I, [_I, _I, _I]),
     "az_temporal_ir": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _D, _P]),
+    "az_sim_ir_pattern_workspace_bytes": (_I, [_I, _I, _I, _I]),
+    "az_sim_ir_pattern": (ctypes.c_int, [_P, _P, ctypes.c_int, _P, _P, _I, _I, _I, _I, _D, _P]),
     "az_error_metrics_workspace_bytes": (_I, [_I, _I, _I]),
     "az_error_metrics": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "az_local_contrast_norm": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
 }
 
 # CUDA kernels enqueued by one successful call of each compute entry point
-KERNELS_PER_CALL = {"az_reproj_loss_fwd": 2, "az_temporal_ir": 3, "az_upsample_soft_argmin_bwd": 3, "az_error_metrics": 2}
+KERNELS_PER_CALL = {"az_reproj_loss_fwd": 2, "az_temporal_ir": 3, "az_upsample_soft_argmin_bwd": 3, "az_error_metrics": 2, "az_sim_ir_pattern": 4}
 
 _lib = None
 launch_count = 0    # C-ABI compute calls issued

@@ -422,3 +422,25 @@ def error_metric_sums(disp_gt, depth_gt, disp_pred, mask, depth_pred=None, focal
         _lib.call("az_error_metrics", _ptr(dg), _ptr(zg), _ptr(dp), _ptr(zp), _ptr(f), _ptr(bl), _ptr(m), _ptr(out),
                   _ptr(ws), B, H, W, _stream())
     return out
+
+
+def sim_ir_pattern(img_ir, img_no_ir, ks: int = 11, threshold: float = 0.005):
+    """get_smoothed_ir_pattern2 (ks > 0) / get_ir_pattern (ks = 0) of datasets/dataset_utils.py on the
+    GPU.  Inputs: CUDA uint8 (raw grey levels) or float64 (already /255) tensors [H,W] or [B,H,W]."""
+    if not (img_ir.is_cuda and img_no_ir.is_cuda) or img_ir.shape != img_no_ir.shape or img_ir.dtype != img_no_ir.dtype:
+        raise ValueError("sim_ir_pattern: two CUDA tensors of the same shape and dtype expected")
+    if img_ir.dtype not in (torch.uint8, torch.float64):
+        raise ValueError("sim_ir_pattern: uint8 or float64 images expected (the reference computes in float64)")
+    squeeze = img_ir.dim() == 2
+    a = (img_ir.unsqueeze(0) if squeeze else img_ir).contiguous()
+    b = (img_no_ir.unsqueeze(0) if squeeze else img_no_ir).contiguous()
+    if a.dim() != 3:
+        raise ValueError("sim_ir_pattern: [H,W] or [B,H,W] expected")
+    B, H, W = a.shape
+    pat = torch.empty((B, H, W), dtype=torch.float32, device=a.device)
+    ws = torch.empty((_lib.query("az_sim_ir_pattern_workspace_bytes", B, H, W, int(ks)),), dtype=torch.uint8,
+                     device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("az_sim_ir_pattern", _ptr(a), _ptr(b), 1 if a.dtype == torch.uint8 else 0, _ptr(pat), _ptr(ws),
+                  B, H, W, int(ks), float(threshold), _stream())
+    return pat[0] if squeeze else pat

@@ -139,6 +139,15 @@ int az_temporal_ir(const uint8_t* frames, float* pattern, void* workspace,
 int az_local_contrast_norm(const float* image, float* normed, float* std, int64_t B, int64_t Cin,
                            int64_t H, int64_t W, int64_t ks, float eps, void* stream);
 
+/* ---- sim-domain IR pattern -- datasets/dataset_utils.py:12-17 (get_ir_pattern, ks = 0)
+ *      and :33-46 (get_smoothed_ir_pattern2, ks > 0: minus the cv2 INTER_AREA down(//ks)-then-up resampling) ----
+ * img_ir, img_no_ir: [B,H,W], uint8 (is_u8 != 0; divided by 255 in float64 as the reference's loader does) or
+ * float64 (is_u8 == 0); pattern: [B,H,W] float32 in {0,1}; float64 arithmetic in OpenCV's summation order.
+ * workspace: az_sim_ir_pattern_workspace_bytes(B,H,W,ks) bytes. */
+int64_t az_sim_ir_pattern_workspace_bytes(int64_t B, int64_t H, int64_t W, int64_t ks);
+int az_sim_ir_pattern(const void* img_ir, const void* img_no_ir, int is_u8, float* pattern, void* workspace,
+                      int64_t B, int64_t H, int64_t W, int64_t ks, double threshold, void* stream);
+
 /* ---- fused error metrics -- utils/cascade_metrics.py:16-57 (compute_err_metric) ----
  * One pass + one 64-byte read instead of seven boolean gathers with .item() syncs.
  * disp_gt, depth_gt, disp_pred: [B,1,H,W]; depth_pred: [B,1,H,W] or NULL (then focal_length*baseline/disp_pred

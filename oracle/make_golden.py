@@ -284,6 +284,42 @@ def gen_err_metrics():
     np.savez_compressed(os.path.join(GOLDEN, "err_metrics.npz"), **out)
 
 
+def gen_sim_ir_pattern():
+    """datasets/dataset_utils.py:get_ir_pattern / get_smoothed_ir_pattern2 called directly (the module's
+    `from configs.config import cfg` needs yacs, which is not installed: a stub module stands in; cfg is
+    not used by the two functions)."""
+    ref_loader.load()
+    stub = types.ModuleType("configs.config")
+    stub.cfg = types.SimpleNamespace()
+    pkg = types.ModuleType("configs")
+    pkg.config = stub
+    saved = {k: sys.modules.get(k) for k in ("configs", "configs.config")}
+    sys.modules["configs"], sys.modules["configs.config"] = pkg, stub
+    sys.path.insert(0, ref_loader.REFERENCE_ROOT)
+    try:
+        du = importlib.import_module("datasets.dataset_utils")
+    finally:
+        sys.path.remove(ref_loader.REFERENCE_ROOT)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    rng = np.random.default_rng(21)
+    out = {}
+    for tag, (h, w) in (("a", (54, 96)), ("b", (77, 121)), ("c", (40, 61))):
+        base = rng.integers(0, 200, size=(h, w))
+        dots = (rng.random((h, w)) < 0.12) * rng.integers(20, 56, size=(h, w))
+        img_u8 = base.astype(np.uint8)
+        ir_u8 = np.clip(base + dots + rng.integers(0, 3, size=(h, w)), 0, 255).astype(np.uint8)
+        img, ir = img_u8 / 255, ir_u8 / 255  # datasets/messytable.py loads PNGs as uint8 and divides by 255
+        out.update({f"{tag}_img_u8": img_u8, f"{tag}_ir_u8": ir_u8,
+                    f"{tag}_p1": du.get_ir_pattern(ir, img),
+                    f"{tag}_p2": du.get_smoothed_ir_pattern2(ir, img),
+                    f"{tag}_p2_k5": du.get_smoothed_ir_pattern2(ir, img, ks=5, threshold=0.01)})
+    np.savez_compressed(os.path.join(GOLDEN, "sim_ir_pattern.npz"), **out)
+
+
 def gen_state_dict_keys():
     """Names and shapes of every state_dict entry of both reference PSMNet variants
     (checkpoint compatibility contract, test.py:341-342 / train.py:155-170)."""
@@ -309,7 +345,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     for fn in (gen_scatter_warp, gen_temporal_ir, gen_reprojection, gen_soft_argmin, gen_psmnet_inline,
-               gen_state_dict_keys, gen_err_metrics):
+               gen_state_dict_keys, gen_err_metrics, gen_sim_ir_pattern):
         print("generating", fn.__name__, flush=True)
         fn()
     for f in sorted(os.listdir(GOLDEN)):

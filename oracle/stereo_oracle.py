@@ -312,6 +312,135 @@ def temporal_ir_pattern(frames: np.ndarray, ks: int = 11, threshold: float = 0.0
 
 
 # ----------------------------------------------------------------------------
+# §8f rank 3  sim-domain IR pattern     datasets/dataset_utils.py:12-46
+# ----------------------------------------------------------------------------
+
+def ir_pattern(img_ir: np.ndarray, img: np.ndarray, threshold: float = 0.005) -> np.ndarray:
+    """dataset_utils.py:12-17 (get_ir_pattern): min-max normalised |ir - no_ir| > threshold."""
+    diff = np.abs(img_ir - img)
+    diff = (diff - np.min(diff)) / (np.max(diff) - np.min(diff))
+    out = np.zeros_like(diff)
+    out[diff > threshold] = 1
+    return out
+
+
+def smoothed_ir_pattern2(img_ir: np.ndarray, img: np.ndarray, ks: int = 11, threshold: float = 0.005,
+                         use_cv2: bool = True) -> np.ndarray:
+    """dataset_utils.py:33-46 (get_smoothed_ir_pattern2): the normalised difference minus its
+    INTER_AREA down(//ks)-then-up resampling, thresholded.  ``use_cv2=False`` runs the numpy
+    restatement of OpenCV's two resize paths below (bit-identical to cv2 4.13 in this image)."""
+    h, w = img_ir.shape
+    hs, ws = int(h // ks), int(w // ks)
+    diff = np.abs(img_ir - img)
+    diff = (diff - np.min(diff)) / (np.max(diff) - np.min(diff))
+    if use_cv2:
+        import cv2
+
+        avg = cv2.resize(diff, (ws, hs), interpolation=cv2.INTER_AREA)
+        avg = cv2.resize(avg, (w, h), interpolation=cv2.INTER_AREA)
+    else:
+        avg = resize_area_up(resize_area_down(diff, ws, hs), w, h)
+    out = np.zeros_like(diff)
+    out[diff - avg > threshold] = 1
+    return out
+
+
+def _area_tab(ssize: int, dsize: int):
+    """OpenCV computeResizeAreaTab (imgproc/resize.cpp): fractional-area weights, stored as float."""
+    import math
+
+    scale = 1.0 / (dsize / ssize)
+    tab = []
+    for dx in range(dsize):
+        fsx1 = dx * scale
+        fsx2 = fsx1 + scale
+        cell = min(scale, ssize - fsx1)
+        sx1, sx2 = math.ceil(fsx1), math.floor(fsx2)
+        sx2 = min(sx2, ssize - 1)
+        sx1 = min(sx1, sx2)
+        if sx1 - fsx1 > 1e-3:
+            tab.append((dx, sx1 - 1, np.float32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            tab.append((dx, sx, np.float32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            tab.append((dx, sx2, np.float32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+    return tab
+
+
+def resize_area_down(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(src, (dw, dh), INTER_AREA) for a float64 image being SHRUNK: the integer-ratio fast
+    path (block sum times a float 1/area) or the general fractional-area path, in OpenCV's summation order."""
+    H, W = src.shape
+    sx_f, sy_f = 1.0 / (dw / W), 1.0 / (dh / H)
+    if abs(sx_f - round(sx_f)) < np.finfo(np.float64).eps and abs(sy_f - round(sy_f)) < np.finfo(np.float64).eps:
+        ix, iy = int(round(sx_f)), int(round(sy_f))
+        scale = np.float64(np.float32(1.0) / np.float32(ix * iy))
+        # resizeAreaFast_: taps in row-major order, summed four at a time (CV_ENABLE_UNROLLED)
+        taps = [src[ky:ky + dh * iy:iy, kx:kx + dw * ix:ix] for ky in range(iy) for kx in range(ix)]
+        dst = np.zeros((dh, dw))
+        k = 0
+        while k + 4 <= len(taps):
+            dst = dst + (((taps[k] + taps[k + 1]) + taps[k + 2]) + taps[k + 3])
+            k += 4
+        while k < len(taps):
+            dst = dst + taps[k]
+            k += 1
+        return dst * scale
+    xt, yt = _area_tab(W, dw), _area_tab(H, dh)
+    sums = {}
+    for dy, sy, beta in yt:
+        buf = np.zeros(dw)
+        for dx, sx, a in xt:
+            buf[dx] = buf[dx] + src[sy, sx] * np.float64(a)
+        sums[dy] = np.float64(beta) * buf if dy not in sums else sums[dy] + np.float64(beta) * buf
+    dst = np.zeros((dh, dw))
+    for dy, row in sums.items():
+        dst[dy] = row
+    return dst
+
+
+def _area_up_coef(ssize: int, dsize: int):
+    """OpenCV's linear-resize coefficient set-up in area mode (INTER_AREA while ENLARGING)."""
+    import math
+
+    inv = dsize / ssize
+    scale = 1.0 / inv
+    ofs, alpha, xmax = [], [], dsize
+    for dx in range(dsize):
+        sx = math.floor(dx * scale)
+        fx = np.float32((dx + 1) - (sx + 1) * inv)
+        fx = np.float32(0) if fx <= 0 else np.float32(fx - np.floor(fx))
+        if sx < 0:
+            fx, sx = np.float32(0), 0
+        if sx + 1 >= ssize:
+            xmax = min(xmax, dx)
+            if sx >= ssize - 1:
+                fx, sx = np.float32(0), ssize - 1
+        ofs.append(sx)
+        alpha.append((np.float32(1) - fx, fx))
+    return ofs, alpha, xmax
+
+
+def resize_area_up(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(src, (dw, dh), INTER_AREA) for a float64 image being ENLARGED (two-tap linear with
+    area-mode coefficients; horizontal pass then vertical pass)."""
+    H, W = src.shape
+    xo, xa, xmax = _area_up_coef(W, dw)
+    yo, ya, _ = _area_up_coef(H, dh)
+    hb = np.zeros((H, dw))
+    for dx in range(dw):
+        if dx < xmax:
+            hb[:, dx] = src[:, xo[dx]] * np.float64(xa[dx][0]) + src[:, xo[dx] + 1] * np.float64(xa[dx][1])
+        else:
+            hb[:, dx] = src[:, xo[dx]] * 1.0
+    dst = np.zeros((dh, dw))
+    for dy in range(dh):
+        s0, s1 = min(max(yo[dy], 0), H - 1), min(max(yo[dy] + 1, 0), H - 1)
+        dst[dy] = hb[s0] * np.float64(ya[dy][0]) + hb[s1] * np.float64(ya[dy][1])
+    return dst
+
+
+# ----------------------------------------------------------------------------
 # §8f rank 4  error metrics            utils/cascade_metrics.py:16-57
 # ----------------------------------------------------------------------------
 

@@ -657,3 +657,27 @@ def test_ops_inside_autocast_compute_in_fp32():
     assert vol.dtype == torch.float32 and torch.equal(vol, so.concat_volume(L.detach(), R, 4))
     (out.sum() + vol.sum()).backward()
     assert cost.grad is not None and L.grad is not None and cost.grad.dtype == torch.float32
+
+
+# --------------------------------------------------------------------------- §8f-3 sim IR pattern
+def test_sim_ir_pattern_golden_and_random(golden):
+    from activezero_b200.datasets import dataset_utils as az_du
+
+    g = golden("sim_ir_pattern")
+    for tag in ("a", "b", "c"):
+        ir, img = gpu(T(g[f"{tag}_ir_u8"])), gpu(T(g[f"{tag}_img_u8"]))
+        assert np.array_equal(az_du.get_ir_pattern(ir, img).cpu().numpy(), g[f"{tag}_p1"])
+        assert np.array_equal(az_du.get_smoothed_ir_pattern2(ir, img).cpu().numpy(), g[f"{tag}_p2"])
+        assert np.array_equal(az_du.get_smoothed_ir_pattern2(ir, img, ks=5, threshold=0.01).cpu().numpy(), g[f"{tag}_p2_k5"])
+        # float64 inputs (already /255) take the same path
+        ir64, img64 = gpu(T(g[f"{tag}_ir_u8"] / 255)), gpu(T(g[f"{tag}_img_u8"] / 255))
+        assert np.array_equal(az_du.get_smoothed_ir_pattern2(ir64, img64).cpu().numpy(), g[f"{tag}_p2"])
+    rng = np.random.default_rng(60)
+    for (h, w, ks) in ((540, 960, 11), (256, 512, 11), (121, 242, 11), (90, 75, 5)):
+        base = rng.integers(0, 200, size=(2, h, w))
+        ir = np.clip(base + (rng.random((2, h, w)) < 0.1) * 40 + rng.integers(0, 3, size=(2, h, w)), 0, 255).astype(np.uint8)
+        img = base.astype(np.uint8)
+        out = az_du.get_smoothed_ir_pattern2(gpu(T(ir)), gpu(T(img)), ks=ks).cpu().numpy()
+        for b in range(2):
+            ref = so.smoothed_ir_pattern2(ir[b] / 255, img[b] / 255, ks=ks)
+            assert np.array_equal(out[b], ref), (h, w, ks, float((out[b] != ref).mean()))

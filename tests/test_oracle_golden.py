@@ -211,3 +211,25 @@ def test_err_metrics(golden):
     for tag, m in (("m1_", m1), ("m2_", m2)):
         for k, v in m.items():
             np.testing.assert_allclose(v, float(g[tag + k]), rtol=1e-7)
+
+
+def test_sim_ir_pattern(golden):
+    """§8f rank 3: restatement (with cv2, and with the numpy restatement of cv2's INTER_AREA paths)
+    against the real get_ir_pattern / get_smoothed_ir_pattern2."""
+    g = golden("sim_ir_pattern")
+    for tag in ("a", "b", "c"):
+        ir, img = g[f"{tag}_ir_u8"] / 255, g[f"{tag}_img_u8"] / 255
+        assert np.array_equal(so.ir_pattern(ir, img), g[f"{tag}_p1"])
+        for use_cv2 in (True, False):
+            assert np.array_equal(so.smoothed_ir_pattern2(ir, img, use_cv2=use_cv2), g[f"{tag}_p2"])
+            assert np.array_equal(so.smoothed_ir_pattern2(ir, img, ks=5, threshold=0.01, use_cv2=use_cv2), g[f"{tag}_p2_k5"])
+
+
+def test_inter_area_restatement_matches_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    for h, w, ks in ((54, 96, 11), (77, 121, 11), (40, 61, 5), (33, 44, 11), (100, 37, 9)):
+        src = rng.random((h, w))
+        small = cv2.resize(src, (w // ks, h // ks), interpolation=cv2.INTER_AREA)
+        assert np.array_equal(so.resize_area_down(src, w // ks, h // ks), small)
+        assert np.array_equal(so.resize_area_up(small, w, h), cv2.resize(small, (w, h), interpolation=cv2.INTER_AREA))
