@@ -51,15 +51,17 @@ __device__ __forceinline__ float bil(const float* __restrict__ plane, const Taps
     return fmaf(t.w11, plane[t.o11], fmaf(t.w10, plane[t.o10], fmaf(t.w01, plane[t.o01], t.w00 * plane[t.o00])));
 }
 
-// Loads the [Dq][fh][fw] footprint of this CTA's output tile; returns the tile origin.
+// Loads the [Dq][fh][fw] footprint of this CTA's output tile.  64 threads walk the fh*fw positions (one
+// integer division each), the 4 groups of 64 interleave over the Dq planes: no div/mod in the inner loop.
 __device__ __forceinline__ void load_tile(const float* __restrict__ low, float* __restrict__ tile, int b, int Dq, int Hq,
                                           int Wq, int h_lo, int w_lo, int fh, int fw, int FHW) {
-    const int n = Dq * fh * fw;
-    for (int t = threadIdx.y * kUTW + threadIdx.x; t < n; t += kUTW * kUTH) {
-        const int q = t / (fh * fw), rem = t - q * fh * fw;
-        const int hh = rem / fw, ww = rem - hh * fw;
-        tile[q * FHW + hh * fw + ww] =
-            __ldg(low + (((size_t)b * Dq + q) * Hq + (h_lo + hh)) * Wq + (w_lo + ww));
+    const int tid = threadIdx.y * kUTW + threadIdx.x;
+    const int npos = fh * fw;
+    const size_t plane = (size_t)Hq * Wq;
+    for (int pos = tid & 63; pos < npos; pos += 64) {
+        const int hh = pos / fw, ww = pos - hh * fw;
+        const float* src = low + (size_t)b * Dq * plane + (size_t)(h_lo + hh) * Wq + (w_lo + ww);
+        for (int q = tid >> 6; q < Dq; q += (kUTW * kUTH) >> 6) tile[q * FHW + pos] = __ldg(src + (size_t)q * plane);
     }
 }
 
