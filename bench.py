@@ -191,7 +191,7 @@ def run_reference(args, rank):
         "e2e": {"value": pairs_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -372,7 +372,7 @@ def run_b200(args, rank, world, local_rank):
             pairs_s, _, cores = time_cpu_reference(3, 1)
             line["cpu_baseline"] = {"value": pairs_s, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "1 pair of the 8-pair batch per step, 3 timed steps after 1 warm-up"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     else:
         clocks.result()
     if world > 1:
@@ -380,7 +380,31 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner to stdout when the communicator is created), so fd 1 is pointed at stderr for the whole run
+    and the JSON line is written to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
