@@ -681,3 +681,19 @@ def test_sim_ir_pattern_golden_and_random(golden):
         for b in range(2):
             ref = so.smoothed_ir_pattern2(ir[b] / 255, img[b] / 255, ks=ks)
             assert np.array_equal(out[b], ref), (h, w, ks, float((out[b] != ref).mean()))
+
+
+def test_baseline_config1_cost_volume_and_regression():
+    """BASELINE config 1, verbatim: cost volume + disparity regression forward on one synthetic 256x512
+    pair, maxdisp 192, against the reference's torch path on the CPU (L,R = randn(1,32,64,128,
+    seed 0), cost = randn(1,192,256,512))."""
+    torch.manual_seed(0)
+    L, R = torch.randn(1, 32, 64, 128), torch.randn(1, 32, 64, 128)
+    cost = torch.randn(1, 192, 256, 512)
+    vol = ops.build_concat_volume(gpu(L), gpu(R), 192 // 4)
+    assert torch.equal(vol.cpu(), so.concat_volume(L, R, 48))          # bit-exact
+    disp = ops.soft_argmin(gpu(cost))
+    ref = so.soft_argmin(cost)                                          # torch CPU, fp32
+    ref64 = _sa_ref64(cost)
+    assert float((disp.cpu().double() - ref64).abs().max()) <= 2e-5
+    assert float((disp.cpu() - ref).abs().max()) <= 1e-4
