@@ -141,8 +141,88 @@ __global__ void __launch_bounds__(kTirTX * kTirTY) tir_pattern_kernel(const doub
 }
 
 // ------------------------------------------------------------------------------------------
-// a12 LCN.  grid = (ceil(W/32), ceil(H/8), B); smem tile (8+ks-1) x (32+ks-1) floats, zero padded.
+// a12 LCN (utils/reprojection.py:175-200): zero-padded ks x ks window mean and POPULATION std, two-pass
+// (mean first, then squared deviations -- the one-pass E[x^2]-mean^2 form cancels catastrophically in
+// near-constant windows).
+// Fast path (ks in {3..13}): a thread owns FOUR adjacent outputs; per window row it reads its 4+ks-1 values
+// as aligned 128-bit shared loads and reuses them for the four windows (12x fewer shared loads than one
+// output per thread).  grid = (ceil(W/128), ceil(H/8), B), block (32, 8); tile (8+ks-1) x (128+16) floats.
 // ------------------------------------------------------------------------------------------
+constexpr int kLcnTW = 128, kLcnTH = 8, kLcnPad = 16;  // pad >= ks-1+3, multiple of 4
+
+template <int KS>
+__global__ void __launch_bounds__(256) lcn_strip_kernel(const float* __restrict__ image, float* __restrict__ normed,
+                                                        float* __restrict__ stdo, int Cin, int H, int W, float eps) {
+    extern __shared__ __align__(16) float ftile[];
+    constexpr int h = KS / 2;
+    constexpr int TW = kLcnTW + kLcnPad, TH = kLcnTH + KS - 1;
+    constexpr int NV = (KS + 3 + 3) / 4;  // float4 vectors covering the 4 + KS - 1 values of a window row
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * kLcnTW, y0 = blockIdx.y * kLcnTH;
+    const float* im = image + (size_t)b * Cin * H * W;  // channel 0 (reprojection.py:184-185)
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int t = tid; t < TW * TH; t += 256) {
+        const int ty = t / TW, tx = t - ty * TW;
+        const int yy = y0 + ty - h, xx = x0 + tx - h;
+        ftile[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + (size_t)yy * W + xx) : 0.f;
+    }
+    __syncthreads();
+    const int xl = threadIdx.x * 4;  // first of this thread's four output columns inside the tile
+    const int y = y0 + threadIdx.y;
+    if (y >= H || x0 + xl >= W) return;
+    const float inv = 1.0f / (float)(KS * KS);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+        float v[NV * 4];
+        const float4* row = reinterpret_cast<const float4*>(ftile + (threadIdx.y + ky) * TW + xl);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const float4 t = row[q];
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < KS; ++k) s[j] += v[j + k];
+    }
+    float mean[4], q2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mean[j] = s[j] * inv;
+    float centre[4];
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+        float v[NV * 4];
+        const float4* row = reinterpret_cast<const float4*>(ftile + (threadIdx.y + ky) * TW + xl);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const float4 t = row[q];
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+        if (ky == h) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) centre[j] = v[j + h];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                const float d = v[j + k] - mean[j];
+                q2[j] = fmaf(d, d, q2[j]);
+            }
+    }
+    const size_t o = (size_t)b * H * W + (size_t)y * W + x0 + xl;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (x0 + xl + j < W) {
+            const float sd = sqrtf(q2[j] * inv);  // population std (unbiased=False, :193-197)
+            normed[o + j] = (centre[j] - mean[j]) / (sd + eps);
+            stdo[o + j] = sd;
+        }
+    }
+}
+
+// generic fallback: one output per thread.  grid = (ceil(W/32), ceil(H/8), B); tile (8+ks-1) x (32+ks-1)
 __global__ void __launch_bounds__(kTirTX * kTirTY) lcn_kernel(const float* __restrict__ image,
                                                              float* __restrict__ normed, float* __restrict__ stdo,
                                                              int Cin, int H, int W, int ks, float eps) {
@@ -151,7 +231,7 @@ __global__ void __launch_bounds__(kTirTX * kTirTY) lcn_kernel(const float* __res
     const int TW = kTirTX + ks - 1, TH = kTirTY + ks - 1;
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kTirTX, y0 = blockIdx.y * kTirTY;
-    const float* im = image + (size_t)b * Cin * H * W;  // channel 0 (reprojection.py:184-185)
+    const float* im = image + (size_t)b * Cin * H * W;
     const int tid = threadIdx.y * kTirTX + threadIdx.x;
     for (int t = tid; t < TW * TH; t += kTirTX * kTirTY) {
         const int ty = t / TW, tx = t - ty * TW;
@@ -172,12 +252,21 @@ __global__ void __launch_bounds__(kTirTX * kTirTY) lcn_kernel(const float* __res
                 const float t = ftile[(threadIdx.y + ky) * TW + threadIdx.x + kx] - mean;
                 q = fmaf(t, t, q);
             }
-        const float sd = sqrtf(q * inv);  // population std (unbiased=False, :193-197)
+        const float sd = sqrtf(q * inv);
         const float v = ftile[(threadIdx.y + h) * TW + threadIdx.x + h];
         const size_t o = (size_t)b * H * W + (size_t)y * W + x;
         normed[o] = (v - mean) / (sd + eps);
         stdo[o] = sd;
     }
+}
+
+template <int KS>
+static int launch_lcn_strip(const float* image, float* normed, float* stdo, int B, int Cin, int H, int W, float eps,
+                            cudaStream_t st) {
+    const size_t smem = (size_t)(kLcnTW + kLcnPad) * (kLcnTH + KS - 1) * sizeof(float);
+    dim3 grid((unsigned)ceil_div(W, kLcnTW), (unsigned)ceil_div(H, kLcnTH), (unsigned)B);
+    lcn_strip_kernel<KS><<<grid, dim3(32, 8), smem, st>>>(image, normed, stdo, Cin, H, W, eps);
+    return (int)cudaGetLastError();
 }
 
 }  // namespace az
@@ -224,10 +313,20 @@ extern "C" int az_local_contrast_norm(const float* image, float* normed, float* 
     if (!image || !normed || !stdo || B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || ks < 1 || (ks % 2) == 0 || ks > 63)
         return AZ_ERR_BAD_ARG;
     if (B > 65535 || H * W >= (1ll << 31)) return AZ_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ks) {
+        case 3: return launch_lcn_strip<3>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        case 5: return launch_lcn_strip<5>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        case 7: return launch_lcn_strip<7>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        case 9: return launch_lcn_strip<9>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        case 11: return launch_lcn_strip<11>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        case 13: return launch_lcn_strip<13>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        default: break;
+    }
     const int TW = kTirTX + (int)ks - 1, TH = kTirTY + (int)ks - 1;
     const size_t smem = (size_t)TW * TH * sizeof(float);
     dim3 grid((unsigned)ceil_div(W, kTirTX), (unsigned)ceil_div(H, kTirTY), (unsigned)B);
-    lcn_kernel<<<grid, dim3(kTirTX, kTirTY), smem, (cudaStream_t)stream>>>(image, normed, stdo, (int)Cin, (int)H, (int)W,
+    lcn_kernel<<<grid, dim3(kTirTX, kTirTY), smem, st>>>(image, normed, stdo, (int)Cin, (int)H, (int)W,
                                                                           (int)ks, eps);
     AZ_LAUNCH_CHECK();
     return 0;
