@@ -697,3 +697,38 @@ def test_baseline_config1_cost_volume_and_regression():
     ref64 = _sa_ref64(cost)
     assert float((disp.cpu().double() - ref64).abs().max()) <= 2e-5
     assert float((disp.cpu() - ref).abs().max()) <= 1e-4
+
+
+def test_hot_path_is_cuda_graph_capturable():
+    """The C-ABI calls only enqueue work on the current stream (no allocation, no sync), so the whole
+    forward hot path can be captured once in a CUDA graph and replayed (launch-bound small batches)."""
+    torch.manual_seed(70)
+    L, R = torch.randn(1, 32, 16, 64, device=DEV), torch.randn(1, 32, 16, 64, device=DEV)
+    cost = torch.randn(1, 48, 64, 256, device=DEV)
+    pL = (torch.rand(1, 1, 64, 256, device=DEV) > 0.5).float()
+    pR = (torch.rand(1, 1, 64, 256, device=DEV) > 0.5).float()
+
+    def step():
+        vol = ops.build_concat_volume(L, R, 12)
+        disp = ops.soft_argmin(cost)
+        loss, vis = ops.reproj_loss(pL, pR, disp, None, ps=11, want_warped=True)
+        return vol, disp, loss, vis
+
+    with torch.no_grad():
+        eager = [t.clone() for t in step()]  # also warms the linspace-table cache (an H2D copy)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            outs = step()
+        for _ in range(3):
+            cost.normal_()                      # new inputs in the captured buffers
+            g.replay()
+        torch.cuda.synchronize()
+        ref = step()
+    for a, b in zip(outs, ref):
+        assert torch.equal(a, b)
+    assert not torch.equal(outs[1], eager[1])   # the replay really consumed the new logits
