@@ -74,4 +74,22 @@ __device__ __forceinline__ float sample_pos(float lin, float shift, float size) 
     return __fmul_rn(__fmaf_rn(__fadd_rn(g, 1.0f), size, -1.0f), 0.5f);
 }
 
+// ---- one axis of a bilinear sample: cell index, weights and zero-padding validity ----------
+struct Axis {
+    int i0;      // floor(pos), clamped to [-2, size] so it is safe to form indices from
+    float w, e;  // w = pos - floor(pos), e = 1 - w
+    bool v0, v1; // corner i0 / i0+1 inside [0,size)
+};
+
+__device__ __forceinline__ Axis make_axis(float pos, int size) {
+    Axis a;
+    const float fl = floorf(pos);
+    a.w = __fsub_rn(pos, fl);
+    a.e = __fsub_rn(1.0f, a.w);
+    a.v0 = (fl >= 0.0f) && (fl <= (float)(size - 1));
+    a.v1 = (fl >= -1.0f) && (fl <= (float)(size - 2));
+    a.i0 = (int)fminf(fmaxf(fl, -2.0f), (float)size);
+    return a;
+}
+
 }  // namespace az

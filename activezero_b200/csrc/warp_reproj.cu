@@ -15,23 +15,6 @@
 
 namespace az {
 
-struct Axis {
-    int i0;      // floor(pos), clamped to [-2, size] so it is safe to form indices from
-    float w, e;  // w = pos - floor(pos), e = 1 - w
-    bool v0, v1; // corner i0 / i0+1 inside [0,size)
-};
-
-__device__ __forceinline__ Axis make_axis(float pos, int size) {
-    Axis a;
-    const float fl = floorf(pos);
-    a.w = __fsub_rn(pos, fl);
-    a.e = __fsub_rn(1.0f, a.w);
-    a.v0 = (fl >= 0.0f) && (fl <= (float)(size - 1));
-    a.v1 = (fl >= -1.0f) && (fl <= (float)(size - 2));
-    a.i0 = (int)fminf(fmaxf(fl, -2.0f), (float)size);
-    return a;
-}
-
 // ------------------------------------------------------------------------------------------
 // a6 forward: out[b,c,i,j].  grid = (ceil(W/256), H, B)
 // ------------------------------------------------------------------------------------------
@@ -342,157 +325,6 @@ __global__ void __launch_bounds__(kFoldThreads) patch_fold_systolic_kernel(const
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Patch loss AND fold image in one pass (what get_reproj_error_patch returns, reprojection.py:99-127).
-// The stand-alone loss and fold kernels both compute every tap Wu of every pixel; here each tap is
-// computed once.  One CTA owns a band of TR consecutive SOURCE rows of one image; per row it stages
-// the blended source rows / target rows like the loss kernel, then every warp walks passes of 64
-// sources (two per lane) like the systolic fold: the tap feeds (a) the squared residual and the two
-// gradient correlations of its own pixel and (b) the shuffle chain whose result H_{i,ky}[x] belongs
-// to output row y = i+ky-p.  Those rows are accumulated in a shared-memory band accumulator
-// (TR+2p rows), in a fixed order; at the end interior rows are stored and the 2p rows shared with
-// the neighbouring band are added with one atomic per element -- two addends per element, hence
-// still deterministic (vis is zero-filled first).
-// smem: Rs[PS][Wp] | Ls[PS][Wp] | Vacc[TR+2p][W]
-// ------------------------------------------------------------------------------------------
-constexpr int kBandRows = 16;
-
-template <int PS>
-__global__ void __launch_bounds__(1024) patch_loss_fold_kernel(
-    const float* __restrict__ tgt, const float* __restrict__ src, const float* __restrict__ disp, float sign,
-    const uint8_t* __restrict__ mask, const float* __restrict__ lin_x, const float* __restrict__ lin_y,
-    float* __restrict__ vis, float* __restrict__ gpre, double* __restrict__ partial, int C, int H, int W) {
-    extern __shared__ __align__(16) float sm[];
-    __shared__ double red[32];
-    constexpr int p = (PS - 1) / 2, OFF = p + 1;
-    constexpr int STEP = 64 - (PS - 1);
-    constexpr int VR = kBandRows + 2 * p;
-    const int band = blockIdx.x, b = blockIdx.y;
-    const int i0 = band * kBandRows;
-    const int Wp = W + 2 * OFF;
-    float* Rs = sm;
-    float* Ls = sm + (size_t)PS * Wp;
-    float* Vacc = Ls + (size_t)PS * Wp;
-    const size_t HW = (size_t)H * W;
-    const int nthreads = blockDim.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
-    const int npass = (W + STEP - 1) / STEP;
-    const float* dimg = disp + (size_t)b * HW;
-
-    double tot = 0.0, cnt = 0.0;
-    for (int c = 0; c < C; ++c) {
-        const float* sp = src + ((size_t)b * C + c) * HW;
-        const float* tp = tgt + ((size_t)b * C + c) * HW;
-        for (int t = threadIdx.x; t < VR * W; t += nthreads) Vacc[t] = 0.f;
-        for (int ii = 0; ii < kBandRows; ++ii) {
-            const int i = i0 + ii;
-            if (i >= H) break;  // block-uniform
-            const Axis ay = make_axis(sample_pos(__ldg(lin_y + i), 0.0f, (float)H), H);
-            const float ay0 = ay.v0 ? ay.e : 0.f, ay1 = ay.v1 ? ay.w : 0.f;
-            __syncthreads();  // previous row's taps are done with Rs/Ls (and Vacc zeroing is visible)
-            for (int xx = threadIdx.x; xx < Wp; xx += nthreads) {
-                const int x = xx - OFF;
-                const bool inx = (x >= 0) && (x < W);
-                int yy = ay.i0 - p;
-                float prev = (inx && yy >= 0 && yy < H) ? __ldg(sp + (size_t)yy * W + x) : 0.f;
-#pragma unroll
-                for (int ky = 0; ky < PS; ++ky) {
-                    ++yy;
-                    const float nxt = (inx && yy >= 0 && yy < H) ? __ldg(sp + (size_t)yy * W + x) : 0.f;
-                    Rs[ky * Wp + xx] = fmaf(ay1, nxt, ay0 * prev);
-                    prev = nxt;
-                    const int ty = i + ky - p;
-                    Ls[ky * Wp + xx] = (inx && ty >= 0 && ty < H) ? __ldg(tp + (size_t)ty * W + x) : 0.f;
-                }
-            }
-            __syncthreads();
-            const float* drow = dimg + (size_t)i * W;
-            const uint8_t* mrow = mask == nullptr ? nullptr : mask + (size_t)b * HW + (size_t)i * W;
-            for (int q = warp; q < npass; q += nwarps) {
-                const int x_out = q * STEP + 2 * lane;  // output column fed by this lane's first source
-                const int j0 = x_out - p;
-                const FoldSrc s0 = fold_src(drow, lin_x, sign, j0, W, OFF, p);
-                const FoldSrc s1 = fold_src(drow, lin_x, sign, j0 + 1, W, OFF, p);
-                // loss ownership: the sources [q*STEP, (q+1)*STEP) belong to this pass (halo lanes only feed the fold)
-                const bool own0 = (2 * lane >= p) && (2 * lane < p + STEP) && (j0 < W);
-                const bool own1 = (2 * lane + 1 >= p) && (2 * lane + 1 < p + STEP) && (j0 + 1 < W);
-                const bool m0 = own0 && (mrow == nullptr || mrow[j0] != 0);
-                const bool m1 = own1 && (mrow == nullptr || mrow[j0 + 1] != 0);
-                // target window of source 0 (source 1: +1); j0 = -1 still has an owned neighbour (j1 = 0)
-                const int lbase = OFF + min(max(j0, -1), W - 1) - p;
-                float sq0 = 0.f, sq1 = 0.f, ga0 = 0.f, ga1 = 0.f, gb0 = 0.f, gb1 = 0.f;
-#pragma unroll 1
-                for (int ky = 0; ky < PS; ++ky) {
-                    const float* r0 = Rs + ky * Wp + s0.base;
-                    const float* r1 = Rs + ky * Wp + s1.base;
-                    const float* ll = Ls + ky * Wp + lbase;
-                    float a0 = r0[0], a1 = r1[0], lv = ll[0];
-                    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-                    for (int k = 0; k < PS; ++k) {
-                        const float n0 = r0[k + 1], n1 = r1[k + 1], ln = ll[k + 1];
-                        const float w0 = fmaf(s0.bx1, n0, s0.bx0 * a0);
-                        const float w1 = fmaf(s1.bx1, n1, s1.bx0 * a1);
-                        const float from_next = __shfl_down_sync(0xffffffffu, acc0, 1);
-                        acc0 = w0 + acc1;
-                        acc1 = w1 + from_next;
-                        const float e0 = w0 - lv, e1 = w1 - ln;  // residuals (target of source 1 is shifted by one)
-                        sq0 = fmaf(e0, e0, sq0); ga0 = fmaf(e0, a0, ga0); gb0 = fmaf(e0, n0, gb0);
-                        sq1 = fmaf(e1, e1, sq1); ga1 = fmaf(e1, a1, ga1); gb1 = fmaf(e1, n1, gb1);
-                        a0 = n0; a1 = n1; lv = ln;
-                    }
-                    if (2 * lane < STEP) {  // H_{i,ky}[x] -> output row y = i+ky-p, band row ii+ky
-                        float* vrow = Vacc + (size_t)(ii + ky) * W;
-                        if (x_out < W) vrow[x_out] += acc0;
-                        if (x_out + 1 < W) vrow[x_out + 1] += acc1;
-                    }
-                }
-                // d(residual)/d(xs) = vx1*B - vx0*A with the validity folded in (bx > 0 <=> corner valid
-                // except for an exactly-zero weight, whose corner then contributes 0 either way)
-                if (own0) {
-                    const Axis ax = make_axis(sample_pos(__ldg(lin_x + j0), __fdiv_rn(sign * __ldg(drow + j0), (float)W), (float)W), W);
-                    const float g = m0 ? ((ax.v1 ? gb0 : 0.f) - (ax.v0 ? ga0 : 0.f)) : 0.f;
-                    if (m0) { tot += (double)sq0; if (c == 0) cnt += 1.0; }
-                    if (gpre != nullptr) {
-                        float* gp = gpre + (size_t)b * HW + (size_t)i * W + j0;
-                        *gp = (c == 0 ? 0.f : *gp) + g;
-                    }
-                }
-                if (own1) {
-                    const Axis ax = make_axis(sample_pos(__ldg(lin_x + j0 + 1), __fdiv_rn(sign * __ldg(drow + j0 + 1), (float)W), (float)W), W);
-                    const float g = m1 ? ((ax.v1 ? gb1 : 0.f) - (ax.v0 ? ga1 : 0.f)) : 0.f;
-                    if (m1) { tot += (double)sq1; if (c == 0) cnt += 1.0; }
-                    if (gpre != nullptr) {
-                        float* gp = gpre + (size_t)b * HW + (size_t)i * W + j0 + 1;
-                        *gp = (c == 0 ? 0.f : *gp) + g;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // flush the band accumulator: rows touched by this band only are stored, shared rows are added
-        float* vimg = vis + ((size_t)b * C + c) * HW;
-        const int rows_here = min(kBandRows, H - i0);
-        for (int t = threadIdx.x; t < VR * W; t += nthreads) {
-            const int vr = t / W, x = t - vr * W;
-            const int y = i0 - p + vr;
-            if (y < 0 || y >= H || vr >= rows_here + 2 * p) continue;
-            const bool from_prev = (y < i0 + p) && (i0 > 0);                       // band-1 also writes row y
-            const bool from_next = (y > i0 + rows_here - 1 - p) && (i0 + rows_here < H);  // band+1 also writes it
-            if (from_prev || from_next) atomicAdd(vimg + (size_t)y * W + x, Vacc[t]);
-            else vimg[(size_t)y * W + x] = Vacc[t];
-        }
-        __syncthreads();
-    }
-    const double bs = block_sum(tot, red);
-    const double bc = block_sum(cnt, red);
-    if (threadIdx.x == 0) {
-        const size_t r = (size_t)b * gridDim.x + band;
-        partial[2 * r] = bs;
-        partial[2 * r + 1] = bc;
-    }
-}
-
 // generic fallback (any odd ps): output-centric gather.  grid = (H, C, B)
 // smem: Bk[ps][Wp] blended source rows | XS[ps][W] sample x of source row i = y+p-ky
 __global__ void __launch_bounds__(512) patch_fold_kernel(const float* __restrict__ src,
@@ -560,6 +392,13 @@ __global__ void __launch_bounds__(512) patch_fold_kernel(const float* __restrict
 
 using namespace az;
 
+namespace az {
+// patch_loss_fold.cu: loss + Fold image in one pass; AZ_ERR_BAD_ARG when the shape does not fit
+int plf_dispatch(const float* tgt, const float* src, const float* disp, float sign, const uint8_t* mask,
+                 const float* lin_x, const float* lin_y, int ps, float* vis, float* gpre, double* partial, int B, int C,
+                 int H, int W, int* nbands_out, cudaStream_t st);
+}
+
 extern "C" int az_warp_fwd(const float* img, const float* disp, const float* lin_x, const float* lin_y, float* out,
                            int64_t B, int64_t C, int64_t H, int64_t W, void* stream) {
     if (!img || !disp || !lin_x || !lin_y || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return AZ_ERR_BAD_ARG;
@@ -602,17 +441,6 @@ extern "C" int az_reproj_loss_fwd(const float* tgt, const float* src, const floa
                                   const uint8_t* mask, const float* lin_x, const float* lin_y, int64_t ps,
                                   float* warped, float* gpre, float* loss_out, double* stats, void* workspace,
                                   int64_t B, int64_t C, int64_t H, int64_t W, void* stream) {
-    if (warped != nullptr && ps > 1) {
-        // the fold image is requested too: one fused pass when it fits, else loss then fold
-        const int64_t pp = (ps - 1) / 2;
-        const size_t need = (2 * (size_t)ps * ((size_t)W + 2 * (pp + 1)) + (size_t)(kBandRows + 2 * pp) * W) * sizeof(float);
-        if (ps > 13 || need > 225 * 1024) {
-            int rc2 = az_reproj_loss_fwd(tgt, src, disp, sign, mask, lin_x, lin_y, ps, nullptr, gpre, loss_out, stats,
-                                         workspace, B, C, H, W, stream);
-            if (rc2 != 0) return rc2;
-            return az_patch_fold(src, disp, sign, lin_x, lin_y, ps, warped, B, C, H, W, stream);
-        }
-    }
     if (!tgt || !src || !disp || !lin_x || !lin_y || !loss_out || !stats || !workspace) return AZ_ERR_BAD_ARG;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || ps < 1 || (ps % 2) == 0) return AZ_ERR_BAD_ARG;
     if (B > 65535 || H * W >= (1ll << 31)) return AZ_ERR_BAD_ARG;
@@ -624,39 +452,24 @@ extern "C" int az_reproj_loss_fwd(const float* tgt, const float* src, const floa
     double* partial = (double*)workspace;
     int rc;
     if (warped != nullptr && ps != 1) {
-        // loss + fold image in one pass (ps in {3..13}); the stand-alone kernels cover everything else
-        const size_t smem_f = smem + (size_t)(kBandRows + 2 * p) * W * sizeof(float);
-        if (ps > 13 || smem_f > 225 * 1024 || H > 65535ll * kBandRows) return AZ_ERR_BAD_ARG;
-        const int step = 64 - (int)(ps - 1);
-        const int npass = (int)((W + step - 1) / step);
-        const int rounds = (npass + 31) / 32;
-        int nwarps = (npass + rounds - 1) / rounds;
-        if (nwarps < 4) nwarps = 4;
-        const int64_t nbands = ceil_div(H, kBandRows);
+        // get_reproj_error_patch: loss + Fold image in one pass (patch_loss_fold.cu) when the shape fits its
+        // shared-memory plan, else the stand-alone loss kernel followed by the stand-alone Fold
         cudaError_t e = cudaMemsetAsync(warped, 0, (size_t)B * C * H * W * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
-        dim3 grid((unsigned)nbands, (unsigned)B);
-#define AZ_FUSED_CASE(N)                                                                                               \
-    case N:                                                                                                            \
-        e = cudaFuncSetAttribute(patch_loss_fold_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);  \
-        if (e != cudaSuccess) return (int)e;                                                                           \
-        patch_loss_fold_kernel<N><<<grid, 32 * nwarps, smem_f, st>>>(tgt, src, disp, sign, mask, lin_x, lin_y, warped,  \
-                                                                     gpre, partial, (int)C, (int)H, (int)W);           \
-        break;
-        switch (ps) {
-            AZ_FUSED_CASE(3)
-            AZ_FUSED_CASE(5)
-            AZ_FUSED_CASE(7)
-            AZ_FUSED_CASE(9)
-            AZ_FUSED_CASE(11)
-            AZ_FUSED_CASE(13)
-            default: return AZ_ERR_BAD_ARG;
+        int nbands = 0;
+        rc = H > (1 << 24) ? AZ_ERR_BAD_ARG
+                           : plf_dispatch(tgt, src, disp, sign, mask, lin_x, lin_y, (int)ps, warped, gpre, partial, (int)B,
+                                          (int)C, (int)H, (int)W, &nbands, st);
+        if (rc == 0) {
+            reproj_finalize_kernel<<<1, 1024, 0, st>>>(partial, B * nbands, (double)(C * ps * ps), loss_out, stats);
+            AZ_LAUNCH_CHECK();
+            return 0;
         }
-#undef AZ_FUSED_CASE
-        AZ_LAUNCH_CHECK();
-        reproj_finalize_kernel<<<1, 1024, 0, st>>>(partial, B * nbands, (double)(C * ps * ps), loss_out, stats);
-        AZ_LAUNCH_CHECK();
-        return 0;
+        if (rc != AZ_ERR_BAD_ARG) return rc;
+        rc = az_reproj_loss_fwd(tgt, src, disp, sign, mask, lin_x, lin_y, ps, nullptr, gpre, loss_out, stats, workspace,
+                                B, C, H, W, stream);
+        if (rc != 0) return rc;
+        return az_patch_fold(src, disp, sign, lin_x, lin_y, ps, warped, B, C, H, W, stream);
     }
 #define AZ_LOSS_CASE(N)                                                                                              \
     case N:                                                                                                          \
