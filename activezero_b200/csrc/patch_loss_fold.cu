@@ -27,7 +27,9 @@
 // Shared-memory bandwidth: lane l owns sources 4l..4l+3, so for a smooth disparity map a plain row
 // layout would make the Rs loads 4-way bank conflicted (stride 4 words).  Rs is therefore stored
 // de-interleaved by column mod 4 ("planes"): element xx lives at plane xx&3, slot xx>>2, and the
-// window walk xx = base+k uses four base pointers per source with compile-time offsets.
+// window walk xx = base+k uses four base pointers per source with compile-time offsets.  Ls and
+// Vacc use the same plane layout, so a lane's 4 adjacent columns are four 64-bit accesses that are
+// each stride-1 across the warp (a 128-bit access at a 32-byte lane stride is 2-way conflicted).
 #include "common.cuh"
 
 namespace az {
@@ -67,11 +69,8 @@ __device__ __forceinline__ u64 lds64(uint32_t addr) {
     asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void lds128(uint32_t addr, u64& a, u64& b) {
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
-}
-__device__ __forceinline__ void sts128(uint32_t addr, u64 a, u64 b) {
-    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
+__device__ __forceinline__ void sts64u(uint32_t addr, u64 v) {
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
 __device__ __forceinline__ void sts64(uint32_t addr, float lo, float hi) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(lo), "f"(hi) : "memory");
@@ -201,13 +200,18 @@ __device__ __forceinline__ void plf_stage_row(const PlfArgs& a, const float* __r
     for (int n = 0; n < np_new; ++n) {
         const int pid = first ? pid0 + n : pid0 + T::NP - 1;
         const int y = 2 * pid - T::YB;
-        const uint32_t rowb = sLs + (uint32_t)((pid % T::LRING) * a.pitchL + T::OFF_L) * 8u;
+        const uint32_t rowb = sLs + (uint32_t)((pid % T::LRING) * a.pitchL) * 8u;
+        const uint32_t ql8 = (uint32_t)a.pitchL * 2u;  // plane stride in bytes
         for (int m = tid2; m < nq; m += nthreads) {
             const int x = 4 * m;
             const float4 u = plf_load4(tp, y, x, H, W, vec);
             const float4 v = plf_load4(tp, y + 1, x, H, W, vec);
-            sts128(rowb + (uint32_t)x * 8u, pk2(u.x, v.x), pk2(u.y, v.y));
-            sts128(rowb + (uint32_t)x * 8u + 16u, pk2(u.z, v.z), pk2(u.w, v.w));
+            const uint32_t sb = rowb + (uint32_t)((T::OFF_L + x) >> 2) * 8u;  // slot of column OFF_L + x
+            // column OFF_L + x + vv lives in plane (OFF_L + vv) & 3, slot (OFF_L + x + vv) >> 2
+            sts64(sb + (uint32_t)((T::OFF_L + 0) & 3) * ql8 + (uint32_t)(((T::OFF_L & 3) + 0) >> 2) * 8u, u.x, v.x);
+            sts64(sb + (uint32_t)((T::OFF_L + 1) & 3) * ql8 + (uint32_t)(((T::OFF_L & 3) + 1) >> 2) * 8u, u.y, v.y);
+            sts64(sb + (uint32_t)((T::OFF_L + 2) & 3) * ql8 + (uint32_t)(((T::OFF_L & 3) + 2) >> 2) * 8u, u.z, v.z);
+            sts64(sb + (uint32_t)((T::OFF_L + 3) & 3) * ql8 + (uint32_t)(((T::OFF_L & 3) + 3) >> 2) * 8u, u.w, v.w);
         }
     }
 }
@@ -253,9 +257,9 @@ __device__ __forceinline__ void plf_taps(const PlfArgs& a, int i, int i0, int ro
         const int pid = pid0 + r;
         // target window: NLW columns x 2 rows
         u64 Lw[T::NLW];
-        const uint32_t la = sLs + (uint32_t)((pid % T::LRING) * a.pitchL + lstart) * 8u;
+        const uint32_t la = sLs + (uint32_t)((pid % T::LRING) * a.pitchL) * 8u + (uint32_t)(lstart >> 2) * 8u;
 #pragma unroll
-        for (int c2 = 0; c2 < T::NLW / 2; ++c2) lds128(la + 16u * c2, Lw[2 * c2], Lw[2 * c2 + 1]);
+        for (int m = 0; m < T::NLW; ++m) Lw[m] = lds64(la + (uint32_t)(m & 3) * (uint32_t)(a.pitchL * 2) + 8u * (m >> 2));
         u64 a2[4], acc2[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -305,10 +309,9 @@ __device__ __forceinline__ void plf_taps(const PlfArgs& a, int i, int i0, int ro
         }
         // Fold ring: rows (2*pid - YB, +1), columns vcol..vcol+3
         if (vlane) {
-            const uint32_t va = sV + (uint32_t)((pid % T::VRING) * a.pitchV + vcol) * 8u;
-            u64 v0, v1, v2, v3;
-            lds128(va, v0, v1);
-            lds128(va + 16u, v2, v3);
+            const uint32_t va = sV + (uint32_t)((pid % T::VRING) * a.pitchV) * 8u + (uint32_t)(vcol >> 2) * 8u;
+            const uint32_t qv8 = (uint32_t)a.pitchV * 2u;  // plane stride in bytes
+            u64 v0 = lds64(va), v1 = lds64(va + qv8), v2 = lds64(va + 2 * qv8), v3 = lds64(va + 3 * qv8);
             v0 = add2(v0, acc2[0]);
             v1 = add2(v1, acc2[1]);
             v2 = add2(v2, acc2[2]);
@@ -343,8 +346,10 @@ __device__ __forceinline__ void plf_taps(const PlfArgs& a, int i, int i0, int ro
                 if (e0) { v0 = pk2(l0, 0.f); v1 = pk2(l1, 0.f); v2 = pk2(l2, 0.f); v3 = pk2(l3, 0.f); }
                 else    { v0 = pk2(0.f, h0); v1 = pk2(0.f, h1); v2 = pk2(0.f, h2); v3 = pk2(0.f, h3); }
             }
-            sts128(va, v0, v1);
-            sts128(va + 16u, v2, v3);
+            sts64u(va, v0);
+            sts64u(va + qv8, v1);
+            sts64u(va + 2 * qv8, v2);
+            sts64u(va + 3 * qv8, v3);
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t)
@@ -383,8 +388,8 @@ __global__ void __launch_bounds__(kPlfMaxThreads, 1) patch_loss_fold_v2_kernel(c
     // shared-memory carve-up (floats)
     const int rsBuf = T::NP * 2 * a.pitchR;
     float* Rs = sm;                                    // [2][NP][4 planes][pitchR/4][2]
-    float* Ls = Rs + 2 * rsBuf;                        // [LRING][pitchL][2]
-    float* Vacc = Ls + T::LRING * 2 * a.pitchL;        // [VRING][pitchV][2]
+    float* Ls = Rs + 2 * rsBuf;                        // [LRING][4 planes][pitchL/4][2]
+    float* Vacc = Ls + T::LRING * 2 * a.pitchL;        // [VRING][4 planes][pitchV/4][2]
     float* PsW = Vacc + T::VRING * 2 * a.pitchV;       // [2][pitchP] horizontal weight of each source
     int* PsC = reinterpret_cast<int*>(PsW + 2 * a.pitchP);  // [2][pitchP] window start << 3 | mask << 2 | edge flags
     float* Gs = reinterpret_cast<float*>(PsC + 2 * a.pitchP);  // [2][G-1][npass*128] gradient partials of groups 1.. (GRAD)
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(kPlfMaxThreads, 1) patch_loss_fold_v2_kernel(c
     bool own[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) own[t] = (li0 + t >= T::P) && (li0 + t < T::P + T::S) && (s0 + t < W);
-    const int lstart = min(q * T::S + li0, a.pitchL - T::NLW);
+    const int lstart = min(q * T::S + li0, (a.pitchL - T::NLW) & ~3);
     const int vcol = q * T::S + li0;
     const bool vlane = (li0 < T::S) && (vcol < a.pitchV);
     const int r_lo = grp * T::NP / a.G, r_hi = (grp + 1) * T::NP / a.G;
@@ -494,7 +499,7 @@ __global__ void __launch_bounds__(kPlfMaxThreads, 1) patch_loss_fold_v2_kernel(c
             const int y = i_last - T::P + 1 + yy;
             if (y < 0 || y >= H) continue;
             const int pid = (y + T::YB) >> 1, half = (y + T::YB) & 1;
-            const float v = Vacc[((pid % T::VRING) * a.pitchV + x) * 2 + half];
+            const float v = Vacc[((pid % T::VRING) * a.pitchV + (x & 3) * (a.pitchV >> 2) + (x >> 2)) * 2 + half];
             const bool shared_row = (i0 > 0 && y < i0 + T::P) || (i_last + 1 < H && y > i_last - T::P);
             if (shared_row) atomicAdd(vimg + (size_t)y * W + x, v);
             else vimg[(size_t)y * W + x] = v;

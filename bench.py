@@ -41,7 +41,8 @@ UNIT = "pairs/s"
 B, C, H, W, D, PS = 8, 32, 544, 960, 192, 11
 HQ, WQ, DQ = H // 4, W // 4, D // 4
 WORKLOAD = (f"config2: PSMNet inference hot path fwd, batch {B} x {H}x{W}, D={D}: concat volume "
-            f"[{B},{2 * C},{DQ},{HQ},{WQ}] + soft-argmin [{B},{D},{H},{W}] + patch reprojection loss ps={PS} (+fold image)")
+            f"[{B},{2 * C},{DQ},{HQ},{WQ}] + soft-argmin [{B},{D},{H},{W}] + patch reprojection loss ps={PS} (+fold image); "
+            f"logits = trilinear upsample of random [{DQ},{HQ},{WQ}] logits as psmnet.py:186-197 produces them")
 
 # algorithmic bytes per launch (SURVEY.md §8d formulas x B pairs), fp32
 ALGO_BYTES = {
@@ -146,9 +147,13 @@ def make_inputs(nb, seed, device="cpu", pin=False):
     g = torch.Generator().manual_seed(seed)
     L = torch.randn(nb, C, HQ, WQ, generator=g)
     R = torch.randn(nb, C, HQ, WQ, generator=g)
+    # The logits PSMNet feeds to softmax are ALWAYS the trilinear upsample of the [1,D/4,H/4,W/4] output of the
+    # 3-D aggregation (nets/psmnet/psmnet.py:186-197), so the synthetic logits are built the same way from
+    # random low-resolution logits: spatially smooth, like the disparity map regressed from them.
     cost = torch.empty(nb, D, H, W)
     for b in range(nb):  # generated per pair to bound the temporary
-        cost[b] = torch.randn(D, H, W, generator=g) * 4.0
+        low = torch.randn(1, 1, DQ, HQ, WQ, generator=g) * 4.0
+        cost[b] = torch.nn.functional.interpolate(low, size=(D, H, W), mode="trilinear", align_corners=False)[0, 0]
     pat_L = (torch.rand(nb, 1, H, W, generator=g) > 0.5).float()
     pat_R = (torch.rand(nb, 1, H, W, generator=g) > 0.5).float()
     mask = torch.rand(nb, 1, H, W, generator=g) > 0.2
