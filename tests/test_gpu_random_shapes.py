@@ -157,3 +157,49 @@ def test_scatter_warp_lcn_tir_random(case):
     ref = so.temporal_ir_pattern(fr)
     pat = ops.temporal_ir_pattern(torch.from_numpy(fr).to(DEV)).cpu().numpy()
     assert (pat != ref).mean() <= 2e-3, (pat != ref).mean()
+
+
+# Shapes chosen for the one-pass loss + Fold kernel (csrc/patch_loss_fold.cu): several strips per row with 1, 2 and
+# 3 warp groups, several bands per image (rows shared between bands), a short last band, W % 4 != 0 (scalar
+# staging), C > 1 with gradients accumulated over channels, smooth / sloped / out-of-range disparities, and a width
+# whose shared-memory plan does not fit (falls back to the stand-alone loss and Fold kernels).
+@pytest.mark.parametrize("shape,ps,kind", [
+    ((1, 1, 40, 300, ), 5, "smooth"), ((2, 2, 70, 260), 13, "random"), ((1, 1, 64, 700), 7, "slope"),
+    ((1, 1, 33, 1000), 11, "random"), ((1, 1, 200, 130), 11, "smooth"), ((3, 1, 150, 131), 9, "random"),
+    ((1, 3, 37, 243), 3, "outside"), ((1, 1, 30, 1200), 11, "slope"), ((2, 1, 23, 480), 11, "edge"),
+])
+def test_patch_loss_fold_strips_bands_groups(shape, ps, kind):
+    B, C, H, W = shape
+    torch.manual_seed(H * W + ps)
+    L, R = torch.rand(B, C, H, W), torch.rand(B, C, H, W)
+    xs = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W).expand(B, 1, H, W)
+    ys = torch.arange(H, dtype=torch.float32).view(1, 1, H, 1).expand(B, 1, H, W)
+    if kind == "smooth":
+        disp = 7.3 + 0.01 * xs + 0.02 * ys
+    elif kind == "slope":
+        disp = 3.0 + 0.4 * xs - 0.1 * ys
+    elif kind == "outside":
+        disp = (torch.rand(B, 1, H, W) - 0.5) * 4.0 * W
+    elif kind == "edge":  # samples landing in the boundary cells x0 = -1 and x0 = W-1
+        disp = torch.where(torch.rand(B, 1, H, W) > 0.5, xs + 0.25, xs - (W - 1) + 0.25 - 1.0).clone()
+    else:
+        disp = torch.rand(B, 1, H, W) * min(64.0, W / 4)
+    disp = disp.contiguous()
+    mask = torch.rand(B, 1, H, W) > 0.3
+    d32 = disp.clone().requires_grad_(True)
+    rl, rvis, rm = so.reproj_error_patch(L, R, d32, mask, ps=ps)
+    rl.backward()
+    dg = disp.to(DEV).requires_grad_(True)
+    loss, vis, mi = az_rp.get_reproj_error_patch(L.to(DEV), R.to(DEV), dg, mask.to(DEV), ps=ps)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), rl.item(), rtol=1e-5)
+    close(vis, rvis)
+    assert torch.equal(mi.cpu(), rm)
+    close(dg.grad, d32.grad)
+    # forward only (no gradient buffers: the other template instance), and determinism
+    with torch.no_grad():
+        l2, v2, _ = az_rp.get_reproj_error_patch(L.to(DEV), R.to(DEV), disp.to(DEV), mask.to(DEV), ps=ps)
+        l3, v3, _ = az_rp.get_reproj_error_patch(L.to(DEV), R.to(DEV), disp.to(DEV), mask.to(DEV), ps=ps)
+    assert l2.item() == l3.item() and torch.equal(v2, v3)
+    np.testing.assert_allclose(l2.item(), rl.item(), rtol=1e-5)
+    close(v2, rvis)
