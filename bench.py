@@ -52,7 +52,7 @@ ALGO_BYTES = {
 }
 
 
-BOUND = {"concat_volume_fwd": "hbm", "soft_argmin_fwd": "hbm", "reproj_patch_loss+fold_fwd": "shared-memory latency/issue"}
+BOUND = {"concat_volume_fwd": "hbm", "soft_argmin_fwd": "hbm", "reproj_patch_loss+fold_fwd": "shared-memory bandwidth (LSU wavefronts)"}
 
 
 def _peaks():
