@@ -99,125 +99,147 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-constexpr int kTirTX = 32, kTirTY = 8;
+constexpr int kTirTX = 32, kTirTY = 8;  // tile of the generic LCN fallback below
 
-// grid = (ceil(W/32), ceil(H/8), B); smem tile (8+ks-1) x (32+ks-1) doubles + row sums
-__global__ void __launch_bounds__(kTirTX * kTirTY) tir_pattern_kernel(const double* __restrict__ diff,
-                                                                     const unsigned long long* __restrict__ minmax,
-                                                                     float* __restrict__ pattern, int H, int W, int ks,
-                                                                     double threshold) {
+// Box blur + threshold.  grid = (ceil(W/64), ceil(H/32), B), 256 threads; separable sliding-window sums:
+//   smem tile (32+ks-1) x (64+ks-1) normalised values (one float64 division per tile element, 1.5x the
+//   image instead of the 3x of a 32x8 tile), then horizontal window sums for runs of 8 outputs per thread,
+//   then vertical window sums for runs of 8 rows per thread.
+constexpr int kTpTW = 64, kTpTH = 32;
+
+__global__ void __launch_bounds__(256) tir_pattern_kernel(const double* __restrict__ diff,
+                                                          const unsigned long long* __restrict__ minmax,
+                                                          float* __restrict__ pattern, int H, int W, int ks,
+                                                          double threshold) {
     extern __shared__ double tile[];
     const int h = ks >> 1;
-    const int TW = kTirTX + ks - 1, TH = kTirTY + ks - 1;
-    double* rows = tile + TW * TH;  // [TH][kTirTX] horizontal window sums
+    const int IW = kTpTW + ks - 1, IH = kTpTH + ks - 1;
+    double* rows = tile + IW * IH;  // [IH][TW] horizontal window sums
     const int b = blockIdx.z;
-    const int x0 = blockIdx.x * kTirTX, y0 = blockIdx.y * kTirTY;
+    const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH;
     const double mn = __longlong_as_double((long long)minmax[2 * b]);
     const double mx = __longlong_as_double((long long)minmax[2 * b + 1]);
     const double range = __dsub_rn(mx, mn);
     const double* d = diff + (size_t)b * H * W;
-    const int tid = threadIdx.y * kTirTX + threadIdx.x;
-    for (int t = tid; t < TW * TH; t += kTirTX * kTirTY) {
-        const int ty = t / TW, tx = t - ty * TW;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < IW * IH; t += 256) {
+        const int ty = t / IW, tx = t - ty * IW;
         const int yy = reflect101(y0 + ty - h, H), xx = reflect101(x0 + tx - h, W);
         tile[t] = fabs(__dsub_rn(d[(size_t)yy * W + xx], mn) / range);  // :113 normalise, :36 abs
     }
     __syncthreads();
-    for (int t = tid; t < TH * kTirTX; t += kTirTX * kTirTY) {
-        const int ty = t / kTirTX, tx = t - ty * kTirTX;
+    for (int it = tid; it < IH * (kTpTW / 8); it += 256) {
+        const int ty = it / (kTpTW / 8), xl = 8 * (it - ty * (kTpTW / 8));
+        const double* r = tile + ty * IW + xl;
         double s = 0.0;
-        for (int k = 0; k < ks; ++k) s += tile[ty * TW + tx + k];
-        rows[t] = s;
+        for (int k = 0; k < ks; ++k) s += r[k];
+        double* o = rows + ty * kTpTW + xl;
+        o[0] = s;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+            s += r[j + ks - 1] - r[j - 1];
+            o[j] = s;
+        }
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x < W && y < H) {
-        double s = 0.0;
-        for (int k = 0; k < ks; ++k) s += rows[(threadIdx.y + k) * kTirTX + threadIdx.x];
-        const double blur = __dmul_rn(s, 1.0 / (double)(ks * ks));
-        const double v = tile[(threadIdx.y + h) * TW + threadIdx.x + h];
-        pattern[(size_t)b * H * W + (size_t)y * W + x] = (__dsub_rn(v, blur) > threshold) ? 1.0f : 0.0f;
+    const int c = tid & (kTpTW - 1), r0 = (tid / kTpTW) * 8;
+    const int x = x0 + c;
+    if (x >= W) return;
+    double s = 0.0;
+    for (int k = 0; k < ks; ++k) s += rows[(r0 + k) * kTpTW + c];
+    const double inv = 1.0 / (double)(ks * ks);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int y = y0 + r0 + r;
+        if (y < H) {
+            const double blur = __dmul_rn(s, inv);
+            const double v = tile[(r0 + r + h) * IW + c + h];
+            pattern[(size_t)b * H * W + (size_t)y * W + x] = (__dsub_rn(v, blur) > threshold) ? 1.0f : 0.0f;
+        }
+        if (r < 7) s += rows[(r0 + r + ks) * kTpTW + c] - rows[(r0 + r) * kTpTW + c];
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// a12 LCN (utils/reprojection.py:175-200): zero-padded ks x ks window mean and POPULATION std, two-pass
-// (mean first, then squared deviations -- the one-pass E[x^2]-mean^2 form cancels catastrophically in
-// near-constant windows).
-// Fast path (ks in {3..13}): a thread owns FOUR adjacent outputs; per window row it reads its 4+ks-1 values
-// as aligned 128-bit shared loads and reuses them for the four windows (12x fewer shared loads than one
-// output per thread).  grid = (ceil(W/128), ceil(H/8), B), block (32, 8); tile (8+ks-1) x (128+16) floats.
+// a12 LCN (utils/reprojection.py:175-200): zero-padded ks x ks window mean and POPULATION std.
+// Fast path (ks in {3..13}): separable sliding-window sums of x and x^2 in FLOAT64.  The one-pass form
+// E[x^2] - mean^2 cancels catastrophically in float32 for near-constant windows (which is why the first
+// version of this kernel made two passes over the ks*ks window: 2 x 81 x 3 float ops per pixel); with the
+// products (exact in double: 24 x 24 bits) and both sums carried in double the relative error of the
+// variance is ~1e-16 * mean^2 / var, below what the float32 two-pass form (and torch's own float32 std)
+// achieves, at ~30 double operations per pixel.  grid = (ceil(W/64), ceil(H/32), B), 256 threads:
+//   phase 1: per tile row, horizontal window sums (s1, s2) for 4 adjacent outputs per thread (slide by one);
+//   phase 2: per column, vertical window sums over runs of 8 rows (slide by one), then the epilogue.
 // ------------------------------------------------------------------------------------------
-constexpr int kLcnTW = 128, kLcnTH = 8, kLcnPad = 16;  // pad >= ks-1+3, multiple of 4
+constexpr int kLsTW = 64, kLsTH = 32, kLsIW = kLsTW + 16;  // input tile pitch: >= TW + ks - 1, multiple of 4
 
 template <int KS>
-__global__ void __launch_bounds__(256) lcn_strip_kernel(const float* __restrict__ image, float* __restrict__ normed,
-                                                        float* __restrict__ stdo, int Cin, int H, int W, float eps) {
-    extern __shared__ __align__(16) float ftile[];
-    constexpr int h = KS / 2;
-    constexpr int TW = kLcnTW + kLcnPad, TH = kLcnTH + KS - 1;
-    constexpr int NV = (KS + 3 + 3) / 4;  // float4 vectors covering the 4 + KS - 1 values of a window row
+__global__ void __launch_bounds__(256) lcn_sep_kernel(const float* __restrict__ image, float* __restrict__ normed,
+                                                      float* __restrict__ stdo, int Cin, int H, int W, float eps) {
+    extern __shared__ __align__(16) unsigned char lraw[];
+    constexpr int h = KS / 2, IH = kLsTH + KS - 1, IWU = kLsTW + KS - 1;
+    constexpr int NV = (KS + 3 + 3) / 4;  // float4 vectors covering the 4 + KS - 1 inputs of four adjacent windows
+    double2* hs = reinterpret_cast<double2*>(lraw);                    // [IH][TW] horizontal (sum x, sum x^2)
+    float* tile = reinterpret_cast<float*>(hs + IH * kLsTW);           // [IH][IW]
     const int b = blockIdx.z;
-    const int x0 = blockIdx.x * kLcnTW, y0 = blockIdx.y * kLcnTH;
+    const int x0 = blockIdx.x * kLsTW, y0 = blockIdx.y * kLsTH;
     const float* im = image + (size_t)b * Cin * H * W;  // channel 0 (reprojection.py:184-185)
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int t = tid; t < TW * TH; t += 256) {
-        const int ty = t / TW, tx = t - ty * TW;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < IH * kLsIW; t += 256) {
+        const int ty = t / kLsIW, tx = t - ty * kLsIW;
         const int yy = y0 + ty - h, xx = x0 + tx - h;
-        ftile[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + (size_t)yy * W + xx) : 0.f;
+        tile[t] = (tx < IWU && yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + (size_t)yy * W + xx) : 0.f;
     }
     __syncthreads();
-    const int xl = threadIdx.x * 4;  // first of this thread's four output columns inside the tile
-    const int y = y0 + threadIdx.y;
-    if (y >= H || x0 + xl >= W) return;
-    const float inv = 1.0f / (float)(KS * KS);
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int ky = 0; ky < KS; ++ky) {
-        float v[NV * 4];
-        const float4* row = reinterpret_cast<const float4*>(ftile + (threadIdx.y + ky) * TW + xl);
+    for (int it = tid; it < IH * (kLsTW / 4); it += 256) {
+        const int ty = it / (kLsTW / 4), xl = 4 * (it - ty * (kLsTW / 4));
+        double d[NV * 4];
+        const float4* row = reinterpret_cast<const float4*>(tile + ty * kLsIW + xl);
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
             const float4 t = row[q];
-            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            d[4 * q] = (double)t.x; d[4 * q + 1] = (double)t.y; d[4 * q + 2] = (double)t.z; d[4 * q + 3] = (double)t.w;
         }
+        double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int k = 0; k < KS; ++k) { s1 += d[k]; s2 = fma(d[k], d[k], s2); }
+        double2* o = hs + ty * kLsTW + xl;
+        o[0] = make_double2(s1, s2);
 #pragma unroll
-            for (int k = 0; k < KS; ++k) s[j] += v[j + k];
+        for (int j = 1; j < 4; ++j) {
+            s1 += d[j + KS - 1] - d[j - 1];
+            s2 += d[j + KS - 1] * d[j + KS - 1] - d[j - 1] * d[j - 1];
+            o[j] = make_double2(s1, s2);
+        }
     }
-    float mean[4], q2[4] = {0.f, 0.f, 0.f, 0.f};
+    __syncthreads();
+    const int c = tid & (kLsTW - 1), r0 = (tid / kLsTW) * 8;  // 4 row groups of 8 rows
+    const int x = x0 + c;
+    if (x >= W) return;
+    const double inv = 1.0 / (double)(KS * KS);
+    double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) mean[j] = s[j] * inv;
-    float centre[4];
-#pragma unroll
-    for (int ky = 0; ky < KS; ++ky) {
-        float v[NV * 4];
-        const float4* row = reinterpret_cast<const float4*>(ftile + (threadIdx.y + ky) * TW + xl);
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-            const float4 t = row[q];
-            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-        }
-        if (ky == h) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) centre[j] = v[j + h];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int k = 0; k < KS; ++k) {
-                const float d = v[j + k] - mean[j];
-                q2[j] = fmaf(d, d, q2[j]);
-            }
+    for (int k = 0; k < KS; ++k) {
+        const double2 v = hs[(r0 + k) * kLsTW + c];
+        s1 += v.x;
+        s2 += v.y;
     }
-    const size_t o = (size_t)b * H * W + (size_t)y * W + x0 + xl;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (x0 + xl + j < W) {
-            const float sd = sqrtf(q2[j] * inv);  // population std (unbiased=False, :193-197)
-            normed[o + j] = (centre[j] - mean[j]) / (sd + eps);
-            stdo[o + j] = sd;
+    for (int r = 0; r < 8; ++r) {
+        const int y = y0 + r0 + r;
+        if (y < H) {
+            const double mean = s1 * inv;
+            const double var = fmax(s2 * inv - mean * mean, 0.0);  // population variance (unbiased=False, :193-197)
+            const float sd = sqrtf((float)var);
+            const float centre = tile[(r0 + r + h) * kLsIW + c + h];
+            const size_t o = (size_t)b * H * W + (size_t)y * W + x;
+            normed[o] = (centre - (float)mean) / (sd + eps);
+            stdo[o] = sd;
+        }
+        if (r < 7) {
+            const double2 add = hs[(r0 + r + KS) * kLsTW + c], sub = hs[(r0 + r) * kLsTW + c];
+            s1 += add.x - sub.x;
+            s2 += add.y - sub.y;
         }
     }
 }
@@ -261,11 +283,13 @@ __global__ void __launch_bounds__(kTirTX * kTirTY) lcn_kernel(const float* __res
 }
 
 template <int KS>
-static int launch_lcn_strip(const float* image, float* normed, float* stdo, int B, int Cin, int H, int W, float eps,
-                            cudaStream_t st) {
-    const size_t smem = (size_t)(kLcnTW + kLcnPad) * (kLcnTH + KS - 1) * sizeof(float);
-    dim3 grid((unsigned)ceil_div(W, kLcnTW), (unsigned)ceil_div(H, kLcnTH), (unsigned)B);
-    lcn_strip_kernel<KS><<<grid, dim3(32, 8), smem, st>>>(image, normed, stdo, Cin, H, W, eps);
+static int launch_lcn_sep(const float* image, float* normed, float* stdo, int B, int Cin, int H, int W, float eps,
+                          cudaStream_t st) {
+    const size_t smem = (size_t)(kLsTH + KS - 1) * (kLsTW * sizeof(double2) + kLsIW * sizeof(float));
+    cudaError_t e = cudaFuncSetAttribute(lcn_sep_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)ceil_div(W, kLsTW), (unsigned)ceil_div(H, kLsTH), (unsigned)B);
+    lcn_sep_kernel<KS><<<grid, 256, smem, st>>>(image, normed, stdo, Cin, H, W, eps);
     return (int)cudaGetLastError();
 }
 
@@ -296,14 +320,14 @@ extern "C" int az_temporal_ir(const uint8_t* frames, float* pattern, void* works
         tir_slope_kernel<1><<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
     }
     AZ_LAUNCH_CHECK();
-    const int TW = kTirTX + (int)ks - 1, TH = kTirTY + (int)ks - 1;
-    const size_t smem = ((size_t)TW * TH + (size_t)TH * kTirTX) * sizeof(double);
+    const int IW = kTpTW + (int)ks - 1, IH = kTpTH + (int)ks - 1;
+    const size_t smem = ((size_t)IW * IH + (size_t)IH * kTpTW) * sizeof(double);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(tir_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    dim3 g2((unsigned)ceil_div(W, kTirTX), (unsigned)ceil_div(H, kTirTY), (unsigned)B);
-    tir_pattern_kernel<<<g2, dim3(kTirTX, kTirTY), smem, st>>>(diff, minmax, pattern, (int)H, (int)W, (int)ks, threshold);
+    dim3 g2((unsigned)ceil_div(W, kTpTW), (unsigned)ceil_div(H, kTpTH), (unsigned)B);
+    tir_pattern_kernel<<<g2, 256, smem, st>>>(diff, minmax, pattern, (int)H, (int)W, (int)ks, threshold);
     AZ_LAUNCH_CHECK();
     return 0;
 }
@@ -315,12 +339,12 @@ extern "C" int az_local_contrast_norm(const float* image, float* normed, float* 
     if (B > 65535 || H * W >= (1ll << 31)) return AZ_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     switch (ks) {
-        case 3: return launch_lcn_strip<3>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
-        case 5: return launch_lcn_strip<5>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
-        case 7: return launch_lcn_strip<7>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
-        case 9: return launch_lcn_strip<9>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
-        case 11: return launch_lcn_strip<11>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
-        case 13: return launch_lcn_strip<13>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        case 3: return launch_lcn_sep<3>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        case 5: return launch_lcn_sep<5>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        case 7: return launch_lcn_sep<7>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        case 9: return launch_lcn_sep<9>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        case 11: return launch_lcn_sep<11>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
+        case 13: return launch_lcn_sep<13>(image, normed, stdo, (int)B, (int)Cin, (int)H, (int)W, eps, st);
         default: break;
     }
     const int TW = kTirTX + (int)ks - 1, TH = kTirTY + (int)ks - 1;

@@ -45,6 +45,134 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const float* __restrict__
     }
 }
 
+// a6 forward, four adjacent pixels per thread (W % 4 == 0, 16-byte aligned rows): one 128-bit disparity load,
+// sixteen independent gathers in flight and one 128-bit store per channel -- the one-pixel form above keeps only
+// ~16 bytes per thread in flight and is bound by the two dependent memory round trips per wave.
+// Same op order as warp_fwd_kernel (bit-identical results).  grid = (ceil(H*W/4/256), B)
+struct Bil4 {
+    float nw[4], ne[4], sw[4], se[4];
+    int o00[4];
+    unsigned m;  // bit 4*t + {0,1,2,3}: corner {00,01,10,11} of pixel t is inside the image
+};
+
+__device__ __forceinline__ Bil4 bil4_setup(const float4 d4, const float4 lx4, const Axis ay, int W) {
+    Bil4 q;
+    const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, lx[4] = {lx4.x, lx4.y, lx4.z, lx4.w};
+    q.m = 0u;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const Axis ax = make_axis(sample_pos(lx[t], __fdiv_rn(dd[t], (float)W), (float)W), W);
+        q.nw[t] = __fmul_rn(ax.e, ay.e);
+        q.ne[t] = __fmul_rn(ax.w, ay.e);
+        q.sw[t] = __fmul_rn(ax.e, ay.w);
+        q.se[t] = __fmul_rn(ax.w, ay.w);
+        q.o00[t] = ay.i0 * W + ax.i0;
+        const unsigned mm = (ax.v0 && ay.v0 ? 1u : 0u) | (ax.v1 && ay.v0 ? 2u : 0u) | (ax.v0 && ay.v1 ? 4u : 0u) |
+                            (ax.v1 && ay.v1 ? 8u : 0u);
+        q.m |= mm << (4 * t);
+    }
+    return q;
+}
+
+__device__ __forceinline__ void bil4_gather(const float* __restrict__ p, const Bil4& q, int W, float (&v00)[4],
+                                            float (&v01)[4], float (&v10)[4], float (&v11)[4]) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const unsigned mm = q.m >> (4 * t);
+        v00[t] = (mm & 1u) ? __ldg(p + q.o00[t]) : 0.f;
+        v01[t] = (mm & 2u) ? __ldg(p + q.o00[t] + 1) : 0.f;
+        v10[t] = (mm & 4u) ? __ldg(p + q.o00[t] + W) : 0.f;
+        v11[t] = (mm & 8u) ? __ldg(p + q.o00[t] + W + 1) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) warp_fwd4_kernel(const float* __restrict__ img, const float* __restrict__ disp,
+                                                        const float* __restrict__ lin_x,
+                                                        const float* __restrict__ lin_y, float* __restrict__ out,
+                                                        int C, int H, int W) {
+    const int HW = H * W;
+    const int p = 4 * (blockIdx.x * 256 + threadIdx.x);
+    if (p >= HW) return;
+    const int b = blockIdx.y;
+    const int i = p / W, j = p - i * W;
+    const float4 d4 = *reinterpret_cast<const float4*>(disp + (size_t)b * HW + p);
+    const float4 lx4 = __ldg(reinterpret_cast<const float4*>(lin_x + j));
+    const Axis ay = make_axis(sample_pos(__ldg(lin_y + i), 0.0f, (float)H), H);
+    const Bil4 q = bil4_setup(d4, lx4, ay, W);
+    for (int c = 0; c < C; ++c) {
+        const float* pc = img + ((size_t)b * C + c) * HW;
+        float v00[4], v01[4], v10[4], v11[4], o[4];
+        bil4_gather(pc, q, W, v00, v01, v10, v11);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float acc = __fmul_rn(v00[t], q.nw[t]);
+            acc = __fmaf_rn(v01[t], q.ne[t], acc);
+            acc = __fmaf_rn(v10[t], q.sw[t], acc);
+            o[t] = __fmaf_rn(v11[t], q.se[t], acc);
+        }
+        *reinterpret_cast<float4*>(out + ((size_t)b * C + c) * HW + p) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// a8 (ps = 1) fused warp + masked squared residual, four adjacent pixels per thread, direct gathers (no
+// shared-memory staging: with a single tap per pixel there is nothing to reuse).  One CTA per image row;
+// writes the warped image (same op order as warp_fwd_kernel: bit-identical to the oracle), the pre-gradient
+// and the per-row partial sums consumed by reproj_finalize_kernel.  grid = (H, B), 256 threads.
+__global__ void __launch_bounds__(256) reproj_ps1_kernel(const float* __restrict__ tgt, const float* __restrict__ src,
+                                                         const float* __restrict__ disp, float sign,
+                                                         const uint8_t* __restrict__ mask,
+                                                         const float* __restrict__ lin_x,
+                                                         const float* __restrict__ lin_y, float* __restrict__ warped,
+                                                         float* __restrict__ gpre, double* __restrict__ partial, int C,
+                                                         int H, int W) {
+    __shared__ double red[32];
+    const int i = blockIdx.x, b = blockIdx.y;
+    const int HW = H * W;
+    const size_t rowbase = (size_t)b * HW + (size_t)i * W;
+    const Axis ay = make_axis(sample_pos(__ldg(lin_y + i), 0.0f, (float)H), H);
+    double tot = 0.0, cnt = 0.0;
+    for (int j = 4 * threadIdx.x; j < W; j += 4 * 256) {
+        float4 d4 = *reinterpret_cast<const float4*>(disp + rowbase + j);
+        d4.x *= sign; d4.y *= sign; d4.z *= sign; d4.w *= sign;
+        const float4 lx4 = __ldg(reinterpret_cast<const float4*>(lin_x + j));
+        const Bil4 q = bil4_setup(d4, lx4, ay, W);
+        const unsigned m4 = mask == nullptr ? 0x01010101u : *reinterpret_cast<const unsigned*>(mask + rowbase + j);
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < C; ++c) {
+            const size_t plane = ((size_t)b * C + c) * HW;
+            float v00[4], v01[4], v10[4], v11[4], o[4];
+            bil4_gather(src + plane, q, W, v00, v01, v10, v11);
+            const float4 t4 = *reinterpret_cast<const float4*>(tgt + plane + (size_t)i * W + j);
+            const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float acc = __fmul_rn(v00[t], q.nw[t]);
+                acc = __fmaf_rn(v01[t], q.ne[t], acc);
+                acc = __fmaf_rn(v10[t], q.sw[t], acc);
+                o[t] = __fmaf_rn(v11[t], q.se[t], acc);
+                if ((m4 >> (8 * t)) & 0xffu) {
+                    const float r = o[t] - tt[t];
+                    tot += (double)(r * r);
+                    g[t] = fmaf(r, ay.e * (v01[t] - v00[t]) + ay.w * (v11[t] - v10[t]), g[t]);
+                }
+            }
+            if (warped != nullptr)
+                *reinterpret_cast<float4*>(warped + plane + (size_t)i * W + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if ((m4 >> (8 * t)) & 0xffu) cnt += 1.0;
+        if (gpre != nullptr) *reinterpret_cast<float4*>(gpre + rowbase + j) = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    const double bs = block_sum(tot, red);
+    const double bc = block_sum(cnt, red);
+    if (threadIdx.x == 0) {
+        const size_t r = (size_t)b * H + i;
+        partial[2 * r] = bs;
+        partial[2 * r + 1] = bc;
+    }
+}
+
 // a6 backward.  gdisp written; gimg accumulated with atomics (zero-filled by the caller).
 __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__ img, const float* __restrict__ disp,
                                                        const float* __restrict__ lin_x,
@@ -403,6 +531,12 @@ extern "C" int az_warp_fwd(const float* img, const float* disp, const float* lin
                            int64_t B, int64_t C, int64_t H, int64_t W, void* stream) {
     if (!img || !disp || !lin_x || !lin_y || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return AZ_ERR_BAD_ARG;
     if (H > 65535 || B > 65535 || H * W >= (1ll << 31)) return AZ_ERR_BAD_ARG;
+    if (W % 4 == 0 && aligned16(img) && aligned16(disp) && aligned16(out) && aligned16(lin_x)) {
+        dim3 grid4((unsigned)ceil_div(H * W / 4, 256), (unsigned)B);
+        warp_fwd4_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>(img, disp, lin_x, lin_y, out, (int)C, (int)H, (int)W);
+        AZ_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid((unsigned)ceil_div(W, 256), (unsigned)H, (unsigned)B);
     warp_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, disp, lin_x, lin_y, out, (int)C, (int)H, (int)W);
     AZ_LAUNCH_CHECK();
@@ -470,6 +604,17 @@ extern "C" int az_reproj_loss_fwd(const float* tgt, const float* src, const floa
                                 B, C, H, W, stream);
         if (rc != 0) return rc;
         return az_patch_fold(src, disp, sign, lin_x, lin_y, ps, warped, B, C, H, W, stream);
+    }
+    if (ps == 1 && W % 4 == 0 && H <= 65535 && aligned16(tgt) && aligned16(src) && aligned16(disp) && aligned16(lin_x) &&
+        (warped == nullptr || aligned16(warped)) && (gpre == nullptr || aligned16(gpre)) &&
+        (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 3u) == 0)) {
+        dim3 grid((unsigned)H, (unsigned)B);
+        reproj_ps1_kernel<<<grid, 256, 0, st>>>(tgt, src, disp, sign, mask, lin_x, lin_y, warped, gpre, partial, (int)C,
+                                               (int)H, (int)W);
+        AZ_LAUNCH_CHECK();
+        reproj_finalize_kernel<<<1, 1024, 0, st>>>(partial, B * H, (double)C, loss_out, stats);
+        AZ_LAUNCH_CHECK();
+        return 0;
     }
 #define AZ_LOSS_CASE(N)                                                                                              \
     case N:                                                                                                          \

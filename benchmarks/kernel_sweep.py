@@ -35,19 +35,30 @@ def peak():
 _flush = None
 
 
-def time_ms(fn, iters=10, warm=3, flush=False):
+def time_ms(fn, iters=10, warm=3, flush=False, graph=False):
+    """Median device time of fn() in ms.  graph=True captures fn into a CUDA graph first and times replays:
+    the image-sized ops run 10-60 us, less than the Python side of an operator call (allocations, ctypes), so
+    timing the eager call would measure the host."""
     global _flush
     if flush and _flush is None:
         _flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)
     for _ in range(warm):
         fn()
+    run = fn
+    if graph:
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        run = g.replay
+        run()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
     torch.cuda.synchronize()
     for a, b in evs:
         if flush:
             _flush.fill_(1)
         a.record()
-        fn()
+        run()
         b.record()
     torch.cuda.synchronize()
     ts = sorted(a.elapsed_time(b) for a, b in evs)
@@ -144,7 +155,7 @@ def sweep(quick):
         d = torch.rand(B, 1, H, W, device=DEV) * 64
         mask = torch.rand(B, 1, H, W, device=DEV) > 0.2
         hw = B * H * W
-        add("warp_fwd", cfg, time_ms(lambda: ops.warp(pR, d), flush=True), 4 * 3 * hw)
+        add("warp_fwd", cfg, time_ms(lambda: ops.warp(pR, d), flush=True, graph=True), 4 * 3 * hw)
         dg = d.clone().requires_grad_(True)
 
         def patch_fb():
@@ -152,27 +163,27 @@ def sweep(quick):
             loss, _ = ops.reproj_loss(pL, pR, dg, mask, ps=PS)
             loss.backward()
 
-        add("reproj_ps1_loss_fwd", cfg, time_ms(lambda: ops.reproj_loss(pL, pR, d, mask, ps=1), flush=True), 4 * 3 * hw + hw)
-        add("reproj_patch_loss_fwd", cfg, time_ms(lambda: ops.reproj_loss(pL, pR, d, mask, ps=PS), flush=True), 4 * 3 * hw + hw)
+        add("reproj_ps1_loss_fwd", cfg, time_ms(lambda: ops.reproj_loss(pL, pR, d, mask, ps=1), flush=True, graph=True), 4 * 3 * hw + hw)
+        add("reproj_patch_loss_fwd", cfg, time_ms(lambda: ops.reproj_loss(pL, pR, d, mask, ps=PS), flush=True, graph=True), 4 * 3 * hw + hw)
         add("reproj_patch_loss_fwd+bwd", cfg, time_ms(patch_fb, flush=True), 4 * 3 * hw + hw + 3 * 4 * hw)
-        add("patch_fold", cfg, time_ms(lambda: ops.patch_fold(pR, d, PS), flush=True), 4 * 3 * hw)
+        add("patch_fold", cfg, time_ms(lambda: ops.patch_fold(pR, d, PS), flush=True, graph=True), 4 * 3 * hw)
         add("reproj_patch_loss+fold_fwd", cfg, time_ms(lambda: ops.reproj_loss(pL, pR, d, mask, ps=PS, want_warped=True),
-                                                       flush=True), 4 * 4 * hw + hw)
+                                                       flush=True, graph=True), 4 * 4 * hw + hw)
         # the same with a SMOOTH disparity field (what a trained network predicts): the per-pixel random
         # disparities above make ~half of the shared-memory wavefronts bank conflicts
         yy, xx = torch.meshgrid(torch.arange(H, device=DEV), torch.arange(W, device=DEV), indexing="ij")
         ds = (20.0 + 30.0 * torch.sin(xx / 97.0) * torch.cos(yy / 61.0) + 0.013 * xx).view(1, 1, H, W).expand(B, 1, H, W).contiguous()
         cfg_s = {**cfg, "disp": "smooth"}
-        add("reproj_patch_loss_fwd", cfg_s, time_ms(lambda: ops.reproj_loss(pL, pR, ds, mask, ps=PS), flush=True), 4 * 3 * hw + hw)
-        add("patch_fold", cfg_s, time_ms(lambda: ops.patch_fold(pR, ds, PS), flush=True), 4 * 3 * hw)
+        add("reproj_patch_loss_fwd", cfg_s, time_ms(lambda: ops.reproj_loss(pL, pR, ds, mask, ps=PS), flush=True, graph=True), 4 * 3 * hw + hw)
+        add("patch_fold", cfg_s, time_ms(lambda: ops.patch_fold(pR, ds, PS), flush=True, graph=True), 4 * 3 * hw)
         add("reproj_patch_loss+fold_fwd", cfg_s, time_ms(lambda: ops.reproj_loss(pL, pR, ds, mask, ps=PS, want_warped=True),
-                                                         flush=True), 4 * 4 * hw + hw)
+                                                         flush=True, graph=True), 4 * 4 * hw + hw)
         di = (torch.rand(B, 1, H, W, device=DEV) * 64).int()
-        add("scatter_warp", cfg, time_ms(lambda: ops.scatter_warp(d, di, check_sign=False), flush=True), 4 * 3 * hw)
-        add("local_contrast_norm", cfg, time_ms(lambda: ops.local_contrast_norm(pL, 9), flush=True), 4 * 3 * hw)
+        add("scatter_warp", cfg, time_ms(lambda: ops.scatter_warp(d, di, check_sign=False), flush=True, graph=True), 4 * 3 * hw)
+        add("local_contrast_norm", cfg, time_ms(lambda: ops.local_contrast_norm(pL, 9), flush=True, graph=True), 4 * 3 * hw)
         T = 7
         fr = torch.randint(0, 255, (B, T, H, W), dtype=torch.uint8, device=DEV)
-        add("temporal_ir", {**cfg, "T": T}, time_ms(lambda: ops.temporal_ir_pattern(fr), flush=True), T * hw + 4 * hw)
+        add("temporal_ir", {**cfg, "T": T}, time_ms(lambda: ops.temporal_ir_pattern(fr), flush=True, graph=True), T * hw + 4 * hw)
     return rows
 
 
