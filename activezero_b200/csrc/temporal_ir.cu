@@ -171,7 +171,11 @@ __global__ void __launch_bounds__(256) tir_pattern_kernel(const double* __restri
 //   phase 1: per tile row, horizontal window sums (s1, s2) for 4 adjacent outputs per thread (slide by one);
 //   phase 2: per column, vertical window sums over runs of 8 rows (slide by one), then the epilogue.
 // ------------------------------------------------------------------------------------------
-constexpr int kLsTW = 64, kLsTH = 32, kLsIW = kLsTW + 16;  // input tile pitch: >= TW + ks - 1, multiple of 4
+constexpr int kLsTW = 64, kLsTH = 32;
+// Phase 1 maps the lanes of a warp to consecutive tile ROWS (each lane slides along its own row), so the row
+// pitches are padded to make the per-lane 16-byte accesses land in distinct bank groups: input tile pitch 84
+// floats (336 B: 336*l mod 128 takes 8 distinct values), sums pitch 65 double2 (1040 B).
+constexpr int kLsIW = kLsTW + 20, kLsHP = kLsTW + 1;
 
 template <int KS>
 __global__ void __launch_bounds__(256) lcn_sep_kernel(const float* __restrict__ image, float* __restrict__ normed,
@@ -179,8 +183,8 @@ __global__ void __launch_bounds__(256) lcn_sep_kernel(const float* __restrict__ 
     extern __shared__ __align__(16) unsigned char lraw[];
     constexpr int h = KS / 2, IH = kLsTH + KS - 1, IWU = kLsTW + KS - 1;
     constexpr int NV = (KS + 3 + 3) / 4;  // float4 vectors covering the 4 + KS - 1 inputs of four adjacent windows
-    double2* hs = reinterpret_cast<double2*>(lraw);                    // [IH][TW] horizontal (sum x, sum x^2)
-    float* tile = reinterpret_cast<float*>(hs + IH * kLsTW);           // [IH][IW]
+    double2* hs = reinterpret_cast<double2*>(lraw);                    // [IH][HP] horizontal (sum x, sum x^2)
+    float* tile = reinterpret_cast<float*>(hs + IH * kLsHP);           // [IH][IW]
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kLsTW, y0 = blockIdx.y * kLsTH;
     const float* im = image + (size_t)b * Cin * H * W;  // channel 0 (reprojection.py:184-185)
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(256) lcn_sep_kernel(const float* __restrict__ 
     }
     __syncthreads();
     for (int it = tid; it < IH * (kLsTW / 4); it += 256) {
-        const int ty = it / (kLsTW / 4), xl = 4 * (it - ty * (kLsTW / 4));
+        const int j4 = it / IH, ty = it - j4 * IH, xl = 4 * j4;
         double d[NV * 4];
         const float4* row = reinterpret_cast<const float4*>(tile + ty * kLsIW + xl);
 #pragma unroll
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(256) lcn_sep_kernel(const float* __restrict__ 
         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
         for (int k = 0; k < KS; ++k) { s1 += d[k]; s2 = fma(d[k], d[k], s2); }
-        double2* o = hs + ty * kLsTW + xl;
+        double2* o = hs + ty * kLsHP + xl;
         o[0] = make_double2(s1, s2);
 #pragma unroll
         for (int j = 1; j < 4; ++j) {
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(256) lcn_sep_kernel(const float* __restrict__ 
     double s1 = 0.0, s2 = 0.0;
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
-        const double2 v = hs[(r0 + k) * kLsTW + c];
+        const double2 v = hs[(r0 + k) * kLsHP + c];
         s1 += v.x;
         s2 += v.y;
     }
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(256) lcn_sep_kernel(const float* __restrict__ 
             stdo[o] = sd;
         }
         if (r < 7) {
-            const double2 add = hs[(r0 + r + KS) * kLsTW + c], sub = hs[(r0 + r) * kLsTW + c];
+            const double2 add = hs[(r0 + r + KS) * kLsHP + c], sub = hs[(r0 + r) * kLsHP + c];
             s1 += add.x - sub.x;
             s2 += add.y - sub.y;
         }
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(kTirTX * kTirTY) lcn_kernel(const float* __res
 template <int KS>
 static int launch_lcn_sep(const float* image, float* normed, float* stdo, int B, int Cin, int H, int W, float eps,
                           cudaStream_t st) {
-    const size_t smem = (size_t)(kLsTH + KS - 1) * (kLsTW * sizeof(double2) + kLsIW * sizeof(float));
+    const size_t smem = (size_t)(kLsTH + KS - 1) * (kLsHP * sizeof(double2) + kLsIW * sizeof(float));
     cudaError_t e = cudaFuncSetAttribute(lcn_sep_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)ceil_div(W, kLsTW), (unsigned)ceil_div(H, kLsTH), (unsigned)B);

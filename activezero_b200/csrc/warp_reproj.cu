@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) warp_fwd4_kernel(const float* __restrict_
 // shared-memory staging: with a single tap per pixel there is nothing to reuse).  One CTA per image row;
 // writes the warped image (same op order as warp_fwd_kernel: bit-identical to the oracle), the pre-gradient
 // and the per-row partial sums consumed by reproj_finalize_kernel.  grid = (H, B), 256 threads.
-__global__ void __launch_bounds__(256) reproj_ps1_kernel(const float* __restrict__ tgt, const float* __restrict__ src,
+__global__ void __launch_bounds__(256, 4) reproj_ps1_kernel(const float* __restrict__ tgt, const float* __restrict__ src,
                                                          const float* __restrict__ disp, float sign,
                                                          const uint8_t* __restrict__ mask,
                                                          const float* __restrict__ lin_x,
