@@ -52,6 +52,10 @@ ALGO_BYTES = {
 }
 
 
+# training hot path per pair: concat fwd+bwd, 3 x soft-argmin fwd+bwd, patch reprojection fwd+bwd
+TRAIN_B, TRAIN_STEPS = 2, 10
+TRAIN_BYTES_PER_PAIR = (2 * 4 * (2 * C * HQ * WQ + 2 * C * DQ * HQ * WQ) + 3 * (4 * (D * H * W + H * W) + 4 * (2 * D * H * W + 2 * H * W))
+                        + 4 * 3 * H * W + H * W + 4 * H * W)
 BOUND = {"concat_volume_fwd": "hbm", "soft_argmin_fwd": "hbm", "reproj_patch_loss+fold_fwd": "shared-memory bandwidth (LSU wavefronts)"}
 
 
@@ -331,7 +335,42 @@ def run_b200(args, rank, world, local_rank):
         ms_fused, ms_fused_e2e = f0.elapsed_time(f1), f1.elapsed_time(f2)
         h2d_fused = h2d - host[2].numel() * 4 + low_host.numel() * 4
 
-    ms_total, ms_e2e, ms_fused, ms_fused_e2e = dist_util.max_over_ranks([ms_total, ms_e2e, ms_fused, ms_fused_e2e], dev)
+        # ---- informational variant: the TRAINING hot path (BASELINE target "fwd/bwd"), forward and backward of
+        # concat volume + three soft-argmin heads (psmnet.py:200-217) + patch reprojection loss on the last head,
+        # at the same frame size, TRAIN_B pairs per step, device-resident.  The upstream gradients of the volume
+        # and of the three heads are synthetic tensors (in the network they come from dres0 and the smooth-L1 loss).
+        del low_dev
+        ms_train = float("nan")
+        if not args.no_train_variant:
+            tb = TRAIN_B
+            with torch.enable_grad():
+                Lt, Rt = L[:tb].clone().requires_grad_(True), R[:tb].clone().requires_grad_(True)
+                heads = [cost[:tb].clone().requires_grad_(True) for _ in range(3)]
+                gvol = torch.randn(tb, 2 * C, DQ, HQ, WQ, device=dev)
+                gheads = [torch.randn(tb, 1, H, W, device=dev) for _ in range(3)]
+
+                def train_step():
+                    for t in [Lt, Rt] + heads:
+                        t.grad = None
+                    vol = ops.build_concat_volume(Lt, Rt, DQ)
+                    d1, d2, d3 = (ops.soft_argmin(c_) for c_ in heads)
+                    loss, _, _ = az_rp.get_reproj_error_patch(pat_L[:tb], pat_R[:tb], d3, mask[:tb], ps=PS)
+                    torch.autograd.backward([vol, d1, d2, d3, loss], [gvol] + gheads + [None])
+
+                for _ in range(3):
+                    train_step()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                t0.record()
+                for _ in range(TRAIN_STEPS):
+                    train_step()
+                t1.record()
+                barrier()
+                ms_train = t0.elapsed_time(t1)
+                del Lt, Rt, heads, gvol, gheads
+
+    ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train = dist_util.max_over_ranks(
+        [ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train], dev)
 
     if rank == 0:
         per_kernel = {}
@@ -373,6 +412,15 @@ def run_b200(args, rank, world, local_rank):
                 "e2e_value": world * B * e2e_steps / (ms_fused_e2e * 1e-3), "h2d_bytes_per_step": h2d_fused, "unit": UNIT},
             "loss_check": loss_val,
         }
+        if not args.no_train_variant:
+            pairs_s = world * TRAIN_B * TRAIN_STEPS / (ms_train * 1e-3)
+            line["variant_train_fwd_bwd"] = {
+                "note": "informational: training hot path at the same frame size -- concat volume fwd+bwd, three "
+                        "soft-argmin heads fwd+bwd, patch reprojection loss (ps=11, with Fold image) fwd+bwd; "
+                        "synthetic upstream gradients; not part of value/e2e",
+                "value": pairs_s, "unit": UNIT, "pairs_per_gpu_per_step": TRAIN_B, "steps": TRAIN_STEPS,
+                "ms_per_step": ms_train / TRAIN_STEPS, "algo_bytes_per_pair": TRAIN_BYTES_PER_PAIR,
+                "hbm_frac": pairs_s / world * TRAIN_BYTES_PER_PAIR / 1e9 / peak}
         if world == 1 and not args.no_cpu_baseline:
             pairs_s, _, cores = time_cpu_reference(3, 1)
             line["cpu_baseline"] = {"value": pairs_s, "unit": UNIT, "cores": cores, "kind": "port",
@@ -416,6 +464,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-variant", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
