@@ -183,6 +183,32 @@ def gen_reprojection():
     np.savez_compressed(os.path.join(GOLDEN, "reprojection.npz"), **out)
 
 
+def gen_reprojection_wide():
+    """get_reproj_error_patch (utils/reprojection.py:99-127) of the REAL reference on frames wide enough for the
+    one-pass loss + Fold kernel to use several strips per row, several bands per image and all its warp groups:
+    Bernoulli IR patterns (they compress), sloped disparities with an out-of-range region and boundary-cell samples."""
+    rp, _ = ref_loader.load()
+    out = {}
+    torch.manual_seed(21)
+    for tag, (B, C, H, W), ps, masked in (("w11", (1, 1, 44, 300), 11, True), ("w7", (1, 2, 30, 260), 7, False)):
+        L = (torch.rand(B, C, H, W) > 0.5).float()
+        R = (torch.rand(B, C, H, W) > 0.5).float()
+        xs = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W).expand(B, 1, H, W)
+        ys = torch.arange(H, dtype=torch.float32).view(1, 1, H, 1).expand(B, 1, H, W)
+        disp = (9.0 + 0.07 * xs + 0.11 * ys + torch.rand(B, 1, H, W)).contiguous()
+        disp[:, :, :5] = xs[:, :, :5] + 0.25          # samples in the boundary cell x0 = -1 / 0
+        disp[:, :, -4:, : W // 2] += 2.0 * W          # far out of range on the left
+        mask = (torch.rand(B, 1, H, W) > 0.3) if masked else None
+        d = disp.clone().requires_grad_(True)
+        loss, vis, mi = rp.get_reproj_error_patch(L, R, d, mask, ps=ps)
+        loss.backward()
+        out.update({f"{tag}_L": _np(L).astype(np.uint8), f"{tag}_R": _np(R).astype(np.uint8), f"{tag}_disp": _np(disp),
+                    f"{tag}_loss": _np(loss), f"{tag}_vis": _np(vis), f"{tag}_gdisp": _np(d.grad)})
+        if masked:
+            out[f"{tag}_maskin"] = _np(mask)
+    np.savez_compressed(os.path.join(GOLDEN, "reprojection_wide.npz"), **out)
+
+
 def gen_scatter_warp():
     assert build_ref.build(force=True), "reference kernel source not found"
     rng = np.random.default_rng(11)
@@ -345,7 +371,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     for fn in (gen_scatter_warp, gen_temporal_ir, gen_reprojection, gen_soft_argmin, gen_psmnet_inline,
-               gen_state_dict_keys, gen_err_metrics, gen_sim_ir_pattern):
+               gen_state_dict_keys, gen_err_metrics, gen_sim_ir_pattern, gen_reprojection_wide):
         print("generating", fn.__name__, flush=True)
         fn()
     for f in sorted(os.listdir(GOLDEN)):

@@ -326,6 +326,19 @@ def test_reproj_patch_golden(golden, tag, img, masked, ps):
     close(d.grad, g[f"{tag}_gdisp"])
 
 
+@pytest.mark.parametrize("tag,ps", [("w11", 11), ("w7", 7)])
+def test_reproj_patch_wide_golden(golden, tag, ps):
+    """The real reference's get_reproj_error_patch on frames several strips / bands wide (reprojection_wide.npz)."""
+    g = golden("reprojection_wide")
+    d = gpu(T(g[f"{tag}_disp"])).requires_grad_(True)
+    mask = gpu(T(g[f"{tag}_maskin"])) if f"{tag}_maskin" in g.files else None
+    loss, vis, _ = az_rp.get_reproj_error_patch(gpu(T(g[f"{tag}_L"]).float()), gpu(T(g[f"{tag}_R"]).float()), d, mask, ps=ps)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g[f"{tag}_loss"], rtol=1e-5)
+    close(vis, g[f"{tag}_vis"])
+    close(d.grad, g[f"{tag}_gdisp"])
+
+
 @pytest.mark.parametrize("shape,ps", [((1, 1, 32, 64), 11), ((2, 1, 19, 45), 7), ((1, 2, 12, 33), 13), ((1, 1, 6, 5), 11)])
 def test_reproj_patch_random(shape, ps):
     torch.manual_seed(10)

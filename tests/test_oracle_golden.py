@@ -90,6 +90,19 @@ def test_reproj_patch(golden, tag, img, masked, ps):
     np.testing.assert_allclose(d.grad.numpy(), g[f"{tag}_gdisp"], rtol=1e-5, atol=1e-9)
 
 
+@pytest.mark.parametrize("tag,ps", [("w11", 11), ("w7", 7)])
+def test_reproj_patch_wide(golden, tag, ps):
+    """Frames several strips wide (oracle/make_golden.py:gen_reprojection_wide, the real reference's output)."""
+    g = golden("reprojection_wide")
+    d = T(g[f"{tag}_disp"]).requires_grad_(True)
+    mask = T(g[f"{tag}_maskin"]) if f"{tag}_maskin" in g.files else None
+    loss, vis, _ = so.reproj_error_patch(T(g[f"{tag}_L"]).float(), T(g[f"{tag}_R"]).float(), d, mask, ps=ps)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g[f"{tag}_loss"], rtol=1e-6)
+    np.testing.assert_allclose(vis.detach().numpy(), g[f"{tag}_vis"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(d.grad.numpy(), g[f"{tag}_gdisp"], rtol=1e-5, atol=1e-9)
+
+
 def test_reproj_patch_empty_mask_is_nan(golden):
     g = golden("reprojection")
     assert np.isnan(g["p5empty_loss"])
