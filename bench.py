@@ -422,9 +422,9 @@ def run_b200(args, rank, world, local_rank):
                 "ms_per_step": ms_train / TRAIN_STEPS, "algo_bytes_per_pair": TRAIN_BYTES_PER_PAIR,
                 "hbm_frac": pairs_s / world * TRAIN_BYTES_PER_PAIR / 1e9 / peak}
         if world == 1 and not args.no_cpu_baseline:
-            pairs_s, _, cores = time_cpu_reference(3, 1)
+            pairs_s, _, cores = time_cpu_reference(12, 1)  # ~10 s of CPU work on the box's host cores
             line["cpu_baseline"] = {"value": pairs_s, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "1 pair of the 8-pair batch per step, 3 timed steps after 1 warm-up"}
+                                    "sample": "1 pair of the 8-pair batch per step, 12 timed steps after 1 warm-up"}
         emit(line)
     else:
         clocks.result()
