@@ -231,6 +231,110 @@ __global__ void __launch_bounds__(256) concat_bwd_scalar_kernel(const float* __r
     gout[((size_t)b * C + c) * HW + hw] = acc;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// channels_last_3d variants ("emit the volume in the layout cuDNN wants").
+// Logical tensor [B,2C,Dq,H,W] with torch.channels_last_3d strides, i.e. memory order
+// [B][Dq][H][W][2C]: the 3-D aggregation that consumes the volume (plain cuDNN, not this library)
+// runs 2-2.6x faster on B200 in this layout (benchmarks/agg_layout_probe.py), and converting an
+// NCDHW volume afterwards costs a second pass over the 401 MB.
+// Forward: a CTA owns 32 consecutive x of one (b, y): it stages the 32 left and 32 + Dq - 1 right
+// feature vectors TRANSPOSED in shared memory (position-major, C floats per position), then for
+// every disparity writes 32 positions x 2C floats = one contiguous 8 KB run with 128-bit streaming
+// stores (LDS.128 -> STG.128, no arithmetic).  grid = (ceil(W/32), H, B).
+// Backward: the same tile; a thread owns (position, four channels), walks the Dq planes with 8
+// independent 128-bit loads in flight (left half: straight down; right half: along the x + i
+// diagonal), fixed order, atomic-free; the sums are transposed through shared memory so that gL / gR
+// are written as coalesced rows.
+// ------------------------------------------------------------------------------------------
+constexpr int kClTX = 32, kClThreads = 256;
+
+__global__ void __launch_bounds__(kClThreads) concat_fwd_ndhwc_kernel(const float* __restrict__ L,
+                                                                    const float* __restrict__ R,
+                                                                    float* __restrict__ vol, int C, int H, int W,
+                                                                    int Dq) {
+    extern __shared__ __align__(16) float smem[];
+    const int P = C + 4;  // pitch of one position (floats): multiple of 4, not of 32
+    float* LsT = smem;                // [kClTX][P]
+    float* RsT = smem + kClTX * P;    // [kClTX + Dq - 1][P]: x0 - (Dq-1) .. x0 + kClTX - 1
+    const int x0 = blockIdx.x * kClTX, y = blockIdx.y, b = blockIdx.z;
+    const int nr = kClTX + Dq - 1;
+    const size_t HW = (size_t)H * W;
+    const float* Lb = L + (size_t)b * C * HW + (size_t)y * W;
+    const float* Rb = R + (size_t)b * C * HW + (size_t)y * W;
+    for (int t = threadIdx.x; t < C * kClTX; t += kClThreads) {
+        const int c = t / kClTX, xl = t - c * kClTX, x = x0 + xl;
+        LsT[xl * P + c] = x < W ? __ldg(Lb + (size_t)c * HW + x) : 0.f;
+    }
+    for (int t = threadIdx.x; t < C * nr; t += kClThreads) {
+        const int c = t / nr, r = t - c * nr, x = x0 - (Dq - 1) + r;
+        RsT[r * P + c] = (x >= 0 && x < W) ? __ldg(Rb + (size_t)c * HW + x) : 0.f;
+    }
+    __syncthreads();
+    const int C4 = C >> 2, Q = 2 * C4;  // float4 per position
+    const int npos = min(kClTX, W - x0);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = 0; d < Dq; ++d) {
+        float4* od = reinterpret_cast<float4*>(vol + ((((size_t)b * Dq + d) * H + y) * W + x0) * (size_t)(2 * C));
+        for (int t = threadIdx.x; t < npos * Q; t += kClThreads) {
+            const int xl = t / Q, q = t - xl * Q;
+            float4 v = zero;
+            if (x0 + xl >= d)
+                v = q < C4 ? *reinterpret_cast<const float4*>(LsT + xl * P + 4 * q)
+                           : *reinterpret_cast<const float4*>(RsT + (xl - d + Dq - 1) * P + 4 * (q - C4));
+            st_stream(od + t, v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kClThreads) concat_bwd_ndhwc_kernel(const float* __restrict__ gvol,
+                                                                    float* __restrict__ gL, float* __restrict__ gR,
+                                                                    int C, int H, int W, int Dq) {
+    extern __shared__ __align__(16) float smem[];  // Ts[2C][kClTX + 1]
+    const int x0 = blockIdx.x * kClTX, y = blockIdx.y, b = blockIdx.z;
+    const int C4 = C >> 2, Q = 2 * C4, C2 = 2 * C;
+    const size_t plane = (size_t)H * W * C2;  // floats between consecutive disparities
+    const float* gb = gvol + ((size_t)b * Dq * H + y) * (size_t)W * C2;
+    for (int t = threadIdx.x; t < kClTX * Q; t += kClThreads) {
+        const int xl = t / Q, q = t - xl * Q, x = x0 + xl;
+        const bool right = q >= C4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x < W && (right ? gR != nullptr : gL != nullptr)) {
+            // left: g[d][x] for d <= x;  right: g[d][x + d] while x + d < W
+            const int nd = right ? min(Dq, W - x) : min(Dq, x + 1);
+            const float* p = gb + (size_t)x * C2 + 4 * q;
+            const size_t step = plane + (right ? (size_t)C2 : 0);
+            int d = 0;
+            for (; d + 8 <= nd; d += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = ld_stream(reinterpret_cast<const float4*>(p + (size_t)(d + k) * step));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+            }
+            for (; d < nd; ++d) {
+                const float4 v = ld_stream(reinterpret_cast<const float4*>(p + (size_t)d * step));
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        float* ts = smem + (4 * q) * (kClTX + 1) + xl;
+        ts[0] = acc.x;
+        ts[kClTX + 1] = acc.y;
+        ts[2 * (kClTX + 1)] = acc.z;
+        ts[3 * (kClTX + 1)] = acc.w;
+    }
+    __syncthreads();
+    const size_t HW = (size_t)H * W;
+    for (int t = threadIdx.x; t < C2 * kClTX; t += kClThreads) {
+        const int ch = t / kClTX, xl = t - ch * kClTX, x = x0 + xl;
+        if (x >= W) continue;
+        float* dst = ch < C ? gL : gR;
+        if (dst == nullptr) continue;
+        const int c = ch < C ? ch : ch - C;
+        dst[((size_t)b * C + c) * HW + (size_t)y * W + x] = smem[ch * (kClTX + 1) + xl];
+    }
+}
+
 }  // namespace az
 
 using namespace az;
@@ -281,6 +385,35 @@ extern "C" int az_concat_volume_bwd(const float* gvol, float* gL, float* gR, int
     }
     dim3 grid((unsigned)ceil_div(H * W, 256), (unsigned)(2 * C), (unsigned)B);
     concat_bwd_scalar_kernel<<<grid, 256, 0, st>>>(gvol, gL, gR, (int)C, (int)H, (int)W, (int)Dq);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int az_concat_volume_fwd_ndhwc(const float* L, const float* R, float* vol, int64_t B, int64_t C, int64_t H,
+                                          int64_t W, int64_t Dq, void* stream) {
+    if (!L || !R || !vol || B <= 0 || C <= 0 || H <= 0 || W <= 0 || Dq <= 0) return AZ_ERR_BAD_ARG;
+    if ((C % 4) != 0 || !aligned16(vol) || B > 65535 || H > 65535 || H * W >= (1ll << 31) / 4) return AZ_ERR_BAD_ARG;
+    const size_t smem = (size_t)(2 * kClTX + Dq - 1) * (size_t)(C + 4) * sizeof(float);
+    if (smem > 200 * 1024) return AZ_ERR_BAD_ARG;
+    cudaError_t e = cudaFuncSetAttribute(concat_fwd_ndhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)ceil_div(W, kClTX), (unsigned)H, (unsigned)B);
+    concat_fwd_ndhwc_kernel<<<grid, kClThreads, smem, (cudaStream_t)stream>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int az_concat_volume_bwd_ndhwc(const float* gvol, float* gL, float* gR, int64_t B, int64_t C, int64_t H,
+                                          int64_t W, int64_t Dq, void* stream) {
+    if (!gvol || B <= 0 || C <= 0 || H <= 0 || W <= 0 || Dq <= 0) return AZ_ERR_BAD_ARG;
+    if ((C % 4) != 0 || !aligned16(gvol) || B > 65535 || H > 65535 || H * W >= (1ll << 31) / 4) return AZ_ERR_BAD_ARG;
+    if (!gL && !gR) return 0;
+    const size_t smem = (size_t)(2 * C) * (kClTX + 1) * sizeof(float);
+    if (smem > 200 * 1024) return AZ_ERR_BAD_ARG;
+    cudaError_t e = cudaFuncSetAttribute(concat_bwd_ndhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)ceil_div(W, kClTX), (unsigned)H, (unsigned)B);
+    concat_bwd_ndhwc_kernel<<<grid, kClThreads, smem, (cudaStream_t)stream>>>(gvol, gL, gR, (int)C, (int)H, (int)W, (int)Dq);
     AZ_LAUNCH_CHECK();
     return 0;
 }

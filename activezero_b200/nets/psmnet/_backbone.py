@@ -134,6 +134,10 @@ class PSMNetBase(nn.Module):
         # False = the reference's dataflow (F.interpolate then soft-argmin on the 401 MB logits);
         # True = the fused upsample+soft-argmin kernel (same result to <= 1e-4 px).
         self.fuse_upsample = False
+        # False = the reference's NCDHW volume; True = the same volume emitted in torch.channels_last_3d memory
+        # format, in which cuDNN runs the 3-D aggregation below without layout passes
+        # (2-2.6x faster on B200, benchmarks/agg_layout_probe.py).  Set it with use_channels_last_3d().
+        self.volume_channels_last = False
         self.feature_extraction = feature_extraction
         self.dres0 = nn.Sequential(convbn_3d(64, 32, 3, 1, 1), nn.ReLU(inplace=True),
                                    convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True))
@@ -161,6 +165,16 @@ class PSMNetBase(nn.Module):
                 m.bias.data.zero_()
 
     # -- the part of forward() after feature extraction -------------------------------------
+    def use_channels_last_3d(self, enable: bool = True):
+        """Emit the cost volume in channels_last_3d and keep the 3-D convolution weights in the same format.
+        Shapes, state_dict keys and values are unchanged (checkpoints load either way); only strides differ."""
+        self.volume_channels_last = bool(enable)
+        fmt = torch.channels_last_3d if enable else torch.contiguous_format
+        for m in self.modules():
+            if isinstance(m, (nn.Conv3d, nn.ConvTranspose3d)):
+                m.weight.data = m.weight.data.contiguous(memory_format=fmt)
+        return self
+
     def _aggregate(self, cost):
         """psmnet.py:167-181: dres0..4 and the three residual classification heads."""
         cost0 = self.dres0(cost)
@@ -191,7 +205,8 @@ class PSMNetBase(nn.Module):
         from ... import ops
 
         H, W = ref_feat.shape[-2:]
-        cost = ops.build_concat_volume(ref_feat, tgt_feat, self.maxdisp // 4)  # replaces psmnet.py:151-165
+        cost = ops.build_concat_volume(ref_feat, tgt_feat, self.maxdisp // 4,  # replaces psmnet.py:151-165
+                                       channels_last=self.volume_channels_last)
         cost1, cost2, cost3 = self._aggregate(cost)
         pred3 = self._disparity_head(cost3, H, W)
         if self.training:

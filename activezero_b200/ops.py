@@ -65,16 +65,21 @@ class ConcatVolumeFn(torch.autograd.Function):
 
     @staticmethod
     @_fwd32
-    def forward(ctx, ref_feat, tgt_feat, num_disp: int):
+    def forward(ctx, ref_feat, tgt_feat, num_disp: int, channels_last: bool = False):
         L = _cuda_f32(ref_feat, "ref_feat")
         R = _cuda_f32(tgt_feat, "tgt_feat")
         if L.shape != R.shape or L.dim() != 4:
             raise ValueError("concat volume: features must both be [B,C,H,W]")
         B, C, H, W = L.shape
-        vol = torch.empty((B, 2 * C, int(num_disp), H, W), dtype=torch.float32, device=L.device)
+        ndhwc = bool(channels_last) and C % 4 == 0
+        vol = torch.empty((B, 2 * C, int(num_disp), H, W), dtype=torch.float32, device=L.device,
+                          memory_format=torch.channels_last_3d if ndhwc else torch.contiguous_format)
         with torch.cuda.device(L.device):
-            _lib.call("az_concat_volume_fwd", _ptr(L), _ptr(R), _ptr(vol), B, C, H, W, int(num_disp), _stream())
+            _lib.call("az_concat_volume_fwd_ndhwc" if ndhwc else "az_concat_volume_fwd", _ptr(L), _ptr(R), _ptr(vol),
+                      B, C, H, W, int(num_disp), _stream())
         ctx.dims = (B, C, H, W, int(num_disp))
+        if channels_last and not ndhwc:  # C not a multiple of 4: torch's layout conversion (still on the device)
+            vol = vol.contiguous(memory_format=torch.channels_last_3d)
         return vol
 
     @staticmethod
@@ -82,17 +87,26 @@ class ConcatVolumeFn(torch.autograd.Function):
     @_bwd
     def backward(ctx, gvol):
         B, C, H, W, Dq = ctx.dims
-        g = _cuda_f32(gvol, "grad_volume")
+        if not isinstance(gvol, torch.Tensor) or not gvol.is_cuda or gvol.dtype != torch.float32:
+            raise ValueError("grad_volume: expected a float32 CUDA tensor")
+        # a gradient that arrives in channels_last_3d (what cuDNN returns for a channels_last_3d input) is consumed
+        # in place; anything else is made NCDHW-contiguous
+        ndhwc = C % 4 == 0 and Dq * H * W > 1 and gvol.is_contiguous(memory_format=torch.channels_last_3d) \
+            and not gvol.is_contiguous()
+        g = gvol if ndhwc else _cuda_f32(gvol, "grad_volume")
         gL = torch.empty((B, C, H, W), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[0] else None
         gR = torch.empty((B, C, H, W), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(g.device):
-            _lib.call("az_concat_volume_bwd", _ptr(g), _ptr(gL), _ptr(gR), B, C, H, W, Dq, _stream())
-        return gL, gR, None
+            _lib.call("az_concat_volume_bwd_ndhwc" if ndhwc else "az_concat_volume_bwd", _ptr(g), _ptr(gL), _ptr(gR),
+                      B, C, H, W, Dq, _stream())
+        return gL, gR, None, None
 
 
-def build_concat_volume(ref_feat, tgt_feat, num_disp: int):
-    """[B,C,H,W] x2 -> [B,2C,num_disp,H,W] (replaces psmnet.py:151-165)."""
-    return ConcatVolumeFn.apply(ref_feat, tgt_feat, num_disp)
+def build_concat_volume(ref_feat, tgt_feat, num_disp: int, channels_last: bool = False):
+    """[B,C,H,W] x2 -> [B,2C,num_disp,H,W] (replaces psmnet.py:151-165).  ``channels_last=True`` returns the
+    same tensor in ``torch.channels_last_3d`` memory format: the values and the shape are
+    unchanged, only the strides differ, and cuDNN's 3-D convolutions consume it without a layout pass."""
+    return ConcatVolumeFn.apply(ref_feat, tgt_feat, num_disp, channels_last)
 
 
 # ----------------------------------------------------------------------------

@@ -72,9 +72,15 @@ def main():
         res["az_ops_ms"] = timed(lambda: net(x, y), args.iters)
         net.fuse_upsample = True
         res["az_ops_fused_upsample_ms"] = timed(lambda: net(x, y), args.iters)
+        # the volume emitted in channels_last_3d (cuDNN then runs the 3-D aggregation without
+        # layout passes); with and without the fused upsample
+        net.use_channels_last_3d(True)
+        res["az_ops_fused_upsample_ndhwc_volume_ms"] = timed(lambda: net(x, y), args.iters)
         net.fuse_upsample = False
+        res["az_ops_ndhwc_volume_ms"] = timed(lambda: net(x, y), args.iters)
+        net.use_channels_last_3d(False)
         saved = ops.build_concat_volume, ops.soft_argmin
-        ops.build_concat_volume, ops.soft_argmin = torch_concat_volume, torch_soft_argmin
+        ops.build_concat_volume, ops.soft_argmin = (lambda a, b, n, channels_last=False: torch_concat_volume(a, b, n)), torch_soft_argmin
         try:
             res["stock_torch_ops_ms"] = timed(lambda: net(x, y), args.iters)
         finally:

@@ -44,6 +44,14 @@ int az_concat_volume_fwd(const float* L, const float* R, float* vol,
 int az_concat_volume_bwd(const float* gvol, float* gL, float* gR,
                          int64_t B, int64_t C, int64_t H, int64_t W, int64_t Dq, void* stream);
 
+/* The same volume and gradient in torch.channels_last_3d memory order [B][Dq][H][W][2C] (SURVEY.md §8f rank 2:
+ * the layout in which cuDNN's 3-D convolutions consume it without transposing; psmnet.py:165-168 is the consumer).
+ * C must be a multiple of 4 and vol / gvol 16-byte aligned. */
+int az_concat_volume_fwd_ndhwc(const float* L, const float* R, float* vol,
+                               int64_t B, int64_t C, int64_t H, int64_t W, int64_t Dq, void* stream);
+int az_concat_volume_bwd_ndhwc(const float* gvol, float* gL, float* gR,
+                               int64_t B, int64_t C, int64_t H, int64_t W, int64_t Dq, void* stream);
+
 /* ---- a3: group-wise correlation volume -- NOT IN THE REFERENCE (parity unpinned) ----
  * vol[b,g,i,y,x] = (1/(C/G)) * sum_{c in group g} L[b,c,y,x]*R[b,c,y,x-i]  (x >= i, else 0); vol: [B,G,Dq,H,W]. */
 int az_gwc_volume_fwd(const float* L, const float* R, float* vol,

@@ -203,3 +203,34 @@ def test_patch_loss_fold_strips_bands_groups(shape, ps, kind):
     assert l2.item() == l3.item() and torch.equal(v2, v3)
     np.testing.assert_allclose(l2.item(), rl.item(), rtol=1e-5)
     close(v2, rvis)
+
+
+# channels_last_3d volume: same values bit for bit, only the strides differ; the gradient is
+# consumed in place when it arrives in channels_last_3d and through the NCDHW kernel otherwise.
+@pytest.mark.parametrize("case", range(12))
+def test_concat_volume_channels_last_3d(case):
+    rng = np.random.default_rng(7000 + case)
+    B, H = int(rng.integers(1, 4)), int(rng.integers(1, 9))
+    W = int(rng.choice([1, 3, 7, 31, 32, 33, 64, 100]))
+    C = int(rng.choice([4, 8, 12, 32]))
+    Dq = int(rng.choice([1, 2, 5, 12, 48, 70]))
+    torch.manual_seed(case)
+    L = torch.randn(B, C, H, W, dtype=torch.float64, requires_grad=True)
+    R = torch.randn(B, C, H, W, dtype=torch.float64, requires_grad=True)
+    vol = so.concat_volume(L, R, Dq)
+    g = torch.randn(vol.shape, dtype=torch.float64)
+    vol.backward(g)
+    for grad_fmt in (torch.channels_last_3d, torch.contiguous_format):
+        Lg = L.detach().float().to(DEV).requires_grad_(True)
+        Rg = R.detach().float().to(DEV).requires_grad_(True)
+        out = ops.build_concat_volume(Lg, Rg, Dq, channels_last=True)
+        assert out.shape == vol.shape and out.is_contiguous(memory_format=torch.channels_last_3d)
+        assert torch.equal(out.detach().cpu(), so.concat_volume(L.detach().float(), R.detach().float(), Dq))
+        out.backward(g.float().to(DEV).contiguous(memory_format=grad_fmt))
+        close(Lg.grad, L.grad)
+        close(Rg.grad, R.grad)
+    # C not a multiple of 4: torch converts the layout, values unchanged
+    L3, R3 = torch.randn(1, 3, 4, 9, device=DEV), torch.randn(1, 3, 4, 9, device=DEV)
+    o3 = ops.build_concat_volume(L3, R3, 5, channels_last=True)
+    assert o3.is_contiguous(memory_format=torch.channels_last_3d)
+    assert torch.equal(o3, ops.build_concat_volume(L3, R3, 5))

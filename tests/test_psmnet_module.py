@@ -120,3 +120,41 @@ def test_psmnet_train_mode_backward():
     assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
     g3 = net.classif3[2].weight.grad
     assert torch.isfinite(g3).all() and float(g3.abs().max()) > 0
+
+
+@pytest.mark.gpu
+def test_psmnet_channels_last_3d_volume_same_predictions_and_gradients():
+    """use_channels_last_3d() changes strides only: same state_dict, same prediction (TF32 off so that the
+    different cuDNN algorithms agree to rounding), and training gradients flow through the in-place
+    channels_last_3d backward of the volume."""
+    torch.manual_seed(3)
+    net = az_psm3.PSMNet(maxdisp=96).cuda().eval()
+    keys = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    x, y = torch.rand(1, 3, 128, 256, device="cuda"), torch.rand(1, 3, 128, 256, device="cuda")
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            p0 = net(x, y)
+            net.use_channels_last_3d(True)
+            vols = []
+            h = net.dres0.register_forward_pre_hook(lambda m, i: vols.append(i[0]))
+            p1 = net(x, y)
+            h.remove()
+        assert vols[0].is_contiguous(memory_format=torch.channels_last_3d) and not vols[0].is_contiguous()
+        assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == keys
+        assert float((p0 - p1).abs().max()) <= 2e-3, float((p0 - p1).abs().max())
+        # gradients: channels_last_3d vs NCDHW volume, same network
+        grads = []
+        for cl in (True, False):
+            net.use_channels_last_3d(cl).train()
+            net.zero_grad(set_to_none=True)
+            xx = torch.cat([x, x.flip(0)]), torch.cat([y, y.flip(0)])
+            torch.manual_seed(5)
+            p3, p2, pa = net(torch.cat([x, x * 0.5]), torch.cat([y, y * 0.5]))
+            (p3.mean() + 0.7 * p2.mean() + 0.5 * pa.mean()).backward()
+            grads.append(net.feature_extraction.firstconv[0][0].weight.grad.clone())
+        scale = float(grads[1].abs().max())
+        assert scale > 0 and float((grads[0] - grads[1]).abs().max()) <= 2e-2 * scale
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
