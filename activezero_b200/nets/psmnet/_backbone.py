@@ -205,8 +205,10 @@ class PSMNetBase(nn.Module):
         from ... import ops
 
         H, W = ref_feat.shape[-2:]
-        cost = ops.build_concat_volume(ref_feat, tgt_feat, self.maxdisp // 4,  # replaces psmnet.py:151-165
-                                       channels_last=self.volume_channels_last)
+        if self.volume_channels_last:
+            cost = ops.build_concat_volume(ref_feat, tgt_feat, self.maxdisp // 4, channels_last=True)
+        else:
+            cost = ops.build_concat_volume(ref_feat, tgt_feat, self.maxdisp // 4)  # replaces psmnet.py:151-165
         cost1, cost2, cost3 = self._aggregate(cost)
         pred3 = self._disparity_head(cost3, H, W)
         if self.training:

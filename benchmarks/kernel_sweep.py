@@ -96,6 +96,12 @@ def sweep(quick):
             add("concat_volume_bwd", cfg, time_ms(lambda: _lib.call(
                 "az_concat_volume_bwd", ops._ptr(vol), ops._ptr(gL), ops._ptr(gR), B, C, Hq, Wq, Dq, ops._stream())),
                 2 * feat_b + vol.numel() * 4)
+            # the same volume / gradient in channels_last_3d memory order
+            add("concat_volume_fwd_ndhwc", cfg, time_ms(lambda: ops.build_concat_volume(L, R, Dq, channels_last=True)),
+                2 * feat_b + vol.numel() * 4)
+            add("concat_volume_bwd_ndhwc", cfg, time_ms(lambda: _lib.call(
+                "az_concat_volume_bwd_ndhwc", ops._ptr(vol), ops._ptr(gL), ops._ptr(gR), B, C, Hq, Wq, Dq, ops._stream())),
+                2 * feat_b + vol.numel() * 4)
             del vol
             # gwc (the volume is 8x smaller: batch it up to stay >> L2)
             gv = ops.build_gwc_volume(L, R, Dq, G)

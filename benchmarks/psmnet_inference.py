@@ -80,7 +80,7 @@ def main():
         res["az_ops_ndhwc_volume_ms"] = timed(lambda: net(x, y), args.iters)
         net.use_channels_last_3d(False)
         saved = ops.build_concat_volume, ops.soft_argmin
-        ops.build_concat_volume, ops.soft_argmin = (lambda a, b, n, channels_last=False: torch_concat_volume(a, b, n)), torch_soft_argmin
+        ops.build_concat_volume, ops.soft_argmin = torch_concat_volume, torch_soft_argmin
         try:
             res["stock_torch_ops_ms"] = timed(lambda: net(x, y), args.iters)
         finally:

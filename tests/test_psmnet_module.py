@@ -130,7 +130,7 @@ def test_psmnet_channels_last_3d_volume_same_predictions_and_gradients():
     torch.manual_seed(3)
     net = az_psm3.PSMNet(maxdisp=96).cuda().eval()
     keys = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
-    x, y = torch.rand(1, 3, 128, 256, device="cuda"), torch.rand(1, 3, 128, 256, device="cuda")
+    x, y = torch.rand(1, 3, 256, 256, device="cuda"), torch.rand(1, 3, 256, 256, device="cuda")  # SPP needs >= 256
     prev = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
@@ -149,7 +149,6 @@ def test_psmnet_channels_last_3d_volume_same_predictions_and_gradients():
         for cl in (True, False):
             net.use_channels_last_3d(cl).train()
             net.zero_grad(set_to_none=True)
-            xx = torch.cat([x, x.flip(0)]), torch.cat([y, y.flip(0)])
             torch.manual_seed(5)
             p3, p2, pa = net(torch.cat([x, x * 0.5]), torch.cat([y, y * 0.5]))
             (p3.mean() + 0.7 * p2.mean() + 0.5 * pa.mean()).backward()
