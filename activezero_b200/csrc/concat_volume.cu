@@ -238,16 +238,16 @@ __global__ void __launch_bounds__(256) concat_bwd_scalar_kernel(const float* __r
 // [B][Dq][H][W][2C]: the 3-D aggregation that consumes the volume (plain cuDNN, not this library)
 // runs 2-2.6x faster on B200 in this layout (benchmarks/agg_layout_probe.py), and converting an
 // NCDHW volume afterwards costs a second pass over the 401 MB.
-// Forward: a CTA owns 32 consecutive x of one (b, y): it stages the 32 left and 32 + Dq - 1 right
+// Forward: a CTA owns 64 consecutive x of one (b, y): it stages the 64 left and 64 + Dq - 1 right
 // feature vectors TRANSPOSED in shared memory (position-major, C floats per position), then for
-// every disparity writes 32 positions x 2C floats = one contiguous 8 KB run with 128-bit streaming
-// stores (LDS.128 -> STG.128, no arithmetic).  grid = (ceil(W/32), H, B).
-// Backward: the same tile; a thread owns (position, four channels), walks the Dq planes with 8
+// every disparity writes 64 positions x 2C floats = one contiguous 16 KB run with 128-bit streaming
+// stores (LDS.128 -> STG.128, no arithmetic).  grid = (ceil(W/64), H, B).
+// Backward: a 32-position tile; a thread owns (position, four channels), walks the Dq planes with 8
 // independent 128-bit loads in flight (left half: straight down; right half: along the x + i
 // diagonal), fixed order, atomic-free; the sums are transposed through shared memory so that gL / gR
 // are written as coalesced rows.
 // ------------------------------------------------------------------------------------------
-constexpr int kClTX = 32, kClThreads = 256;
+constexpr int kClTX = 64, kClTXB = 32, kClThreads = 256;  // positions per CTA: forward (8-16 KB store runs) / backward
 
 __global__ void __launch_bounds__(kClThreads) concat_fwd_ndhwc_kernel(const float* __restrict__ L,
                                                                     const float* __restrict__ R,
@@ -274,8 +274,43 @@ __global__ void __launch_bounds__(kClThreads) concat_fwd_ndhwc_kernel(const floa
     const int C4 = C >> 2, Q = 2 * C4;  // float4 per position
     const int npos = min(kClTX, W - x0);
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* vrow = vol + (((size_t)b * Dq * H + y) * W + x0) * (size_t)(2 * C);  // d = 0
+    const size_t dstep = (size_t)H * W * (2 * C);
+    if (Q <= kClThreads && (kClThreads % Q) == 0 && kClTX * Q <= 4 * kClThreads &&
+        ((kClThreads / Q) >= kClTX || (kClTX % (kClThreads / Q)) == 0)) {
+        // fast path (C = 4, 8, 16, 32, 64, 128): a thread keeps its channel quad q and walks <= 4 positions,
+        // no integer division in the sweep; the left-half value does not depend on d and stays in registers
+        const int q = threadIdx.x % Q, xstep = kClThreads / Q, nk = xstep >= kClTX ? 1 : kClTX / xstep;
+        const bool left = q < C4;
+        float4 vl[4];
+        const float* rp[4];
+        int xs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xl = threadIdx.x / Q + k * xstep;
+            xs[k] = (k < nk && xl < npos) ? x0 + xl : -1;  // -1: nothing to write
+            vl[k] = zero;
+            rp[k] = RsT;
+            if (xs[k] >= 0) {
+                if (left) vl[k] = *reinterpret_cast<const float4*>(LsT + xl * P + 4 * q);
+                else rp[k] = RsT + (xl + Dq - 1) * P + 4 * (q - C4);
+            }
+        }
+        for (int d = 0; d < Dq; ++d) {
+            float4* od = reinterpret_cast<float4*>(vrow + (size_t)d * dstep) + threadIdx.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (xs[k] >= 0) {
+                    float4 v = zero;
+                    if (xs[k] >= d) v = left ? vl[k] : *reinterpret_cast<const float4*>(rp[k] - d * P);
+                    st_stream(od + k * kClThreads, v);
+                }
+            }
+        }
+        return;
+    }
     for (int d = 0; d < Dq; ++d) {
-        float4* od = reinterpret_cast<float4*>(vol + ((((size_t)b * Dq + d) * H + y) * W + x0) * (size_t)(2 * C));
+        float4* od = reinterpret_cast<float4*>(vrow + (size_t)d * dstep);
         for (int t = threadIdx.x; t < npos * Q; t += kClThreads) {
             const int xl = t / Q, q = t - xl * Q;
             float4 v = zero;
@@ -290,12 +325,12 @@ __global__ void __launch_bounds__(kClThreads) concat_fwd_ndhwc_kernel(const floa
 __global__ void __launch_bounds__(kClThreads) concat_bwd_ndhwc_kernel(const float* __restrict__ gvol,
                                                                     float* __restrict__ gL, float* __restrict__ gR,
                                                                     int C, int H, int W, int Dq) {
-    extern __shared__ __align__(16) float smem[];  // Ts[2C][kClTX + 1]
-    const int x0 = blockIdx.x * kClTX, y = blockIdx.y, b = blockIdx.z;
+    extern __shared__ __align__(16) float smem[];  // Ts[2C][kClTXB + 1]
+    const int x0 = blockIdx.x * kClTXB, y = blockIdx.y, b = blockIdx.z;
     const int C4 = C >> 2, Q = 2 * C4, C2 = 2 * C;
     const size_t plane = (size_t)H * W * C2;  // floats between consecutive disparities
     const float* gb = gvol + ((size_t)b * Dq * H + y) * (size_t)W * C2;
-    for (int t = threadIdx.x; t < kClTX * Q; t += kClThreads) {
+    for (int t = threadIdx.x; t < kClTXB * Q; t += kClThreads) {
         const int xl = t / Q, q = t - xl * Q, x = x0 + xl;
         const bool right = q >= C4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -317,21 +352,21 @@ __global__ void __launch_bounds__(kClThreads) concat_bwd_ndhwc_kernel(const floa
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
         }
-        float* ts = smem + (4 * q) * (kClTX + 1) + xl;
+        float* ts = smem + (4 * q) * (kClTXB + 1) + xl;
         ts[0] = acc.x;
-        ts[kClTX + 1] = acc.y;
-        ts[2 * (kClTX + 1)] = acc.z;
-        ts[3 * (kClTX + 1)] = acc.w;
+        ts[kClTXB + 1] = acc.y;
+        ts[2 * (kClTXB + 1)] = acc.z;
+        ts[3 * (kClTXB + 1)] = acc.w;
     }
     __syncthreads();
     const size_t HW = (size_t)H * W;
-    for (int t = threadIdx.x; t < C2 * kClTX; t += kClThreads) {
-        const int ch = t / kClTX, xl = t - ch * kClTX, x = x0 + xl;
+    for (int t = threadIdx.x; t < C2 * kClTXB; t += kClThreads) {
+        const int ch = t / kClTXB, xl = t - ch * kClTXB, x = x0 + xl;
         if (x >= W) continue;
         float* dst = ch < C ? gL : gR;
         if (dst == nullptr) continue;
         const int c = ch < C ? ch : ch - C;
-        dst[((size_t)b * C + c) * HW + (size_t)y * W + x] = smem[ch * (kClTX + 1) + xl];
+        dst[((size_t)b * C + c) * HW + (size_t)y * W + x] = smem[ch * (kClTXB + 1) + xl];
     }
 }
 
@@ -408,11 +443,11 @@ extern "C" int az_concat_volume_bwd_ndhwc(const float* gvol, float* gL, float* g
     if (!gvol || B <= 0 || C <= 0 || H <= 0 || W <= 0 || Dq <= 0) return AZ_ERR_BAD_ARG;
     if ((C % 4) != 0 || !aligned16(gvol) || B > 65535 || H > 65535 || H * W >= (1ll << 31) / 4) return AZ_ERR_BAD_ARG;
     if (!gL && !gR) return 0;
-    const size_t smem = (size_t)(2 * C) * (kClTX + 1) * sizeof(float);
+    const size_t smem = (size_t)(2 * C) * (kClTXB + 1) * sizeof(float);
     if (smem > 200 * 1024) return AZ_ERR_BAD_ARG;
     cudaError_t e = cudaFuncSetAttribute(concat_bwd_ndhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid((unsigned)ceil_div(W, kClTX), (unsigned)H, (unsigned)B);
+    dim3 grid((unsigned)ceil_div(W, kClTXB), (unsigned)H, (unsigned)B);
     concat_bwd_ndhwc_kernel<<<grid, kClThreads, smem, (cudaStream_t)stream>>>(gvol, gL, gR, (int)C, (int)H, (int)W, (int)Dq);
     AZ_LAUNCH_CHECK();
     return 0;
