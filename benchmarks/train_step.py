@@ -108,6 +108,8 @@ def main():
     ap.add_argument("--width", type=int, default=512)
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--no-real", action="store_true", help="config 3 only (skip the real-domain step)")
+    ap.add_argument("--channels-last-3d", action="store_true",
+                    help="emit the cost volume in channels_last_3d (SURVEY 8f rank 2, layout clause)")
     ap.add_argument("--fuse-upsample", action="store_true",
                     help="use the fused trilinear-upsample + soft-argmin kernel for the three heads (SURVEY §8f-1)")
     args = ap.parse_args()
@@ -119,6 +121,8 @@ def main():
     torch.manual_seed(1)  # cfg.SOLVER.SEED, configs/config.py:100
     model = PSMNet(maxdisp=MAX_DISP).to(dev)
     model.fuse_upsample = args.fuse_upsample
+    if args.channels_last_3d:
+        model.use_channels_last_3d(True)
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
     opt = torch.optim.Adam(model.parameters(), lr=2e-4, betas=(0.9, 0.999))  # configs/config.py:88
@@ -157,7 +161,8 @@ def main():
             "steps": args.steps, "ms_per_iteration": ms / args.steps, "scaling": "weak",
             "config": {"workload": f"config{'3' if args.no_real else '4'}: PSMNet_3 train step {args.height}x{args.width}, "
                                    f"D={MAX_DISP}, batch {args.batch}/GPU, patch reproj ps={PATCH}, T={args.frames}",
-                       "ddp": world > 1, "fuse_upsample": args.fuse_upsample},
+                       "ddp": world > 1, "fuse_upsample": args.fuse_upsample,
+                       "channels_last_3d": args.channels_last_3d},
             "final_loss": float(last)}), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
