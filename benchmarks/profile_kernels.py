@@ -31,6 +31,8 @@ def main():
     for it in range(2):
         vol = ops.build_concat_volume(L, R, Dq)
         vol.backward(torch.ones_like(vol))
+        volc = ops.build_concat_volume(L, R, Dq, channels_last=True)  # channels_last_3d order, SURVEY 8f rank 2
+        volc.backward(torch.ones_like(volc))
         gv = ops.build_gwc_volume(L, R, Dq, 8)
         gv.backward(torch.ones_like(gv))
         disp = ops.soft_argmin(cost)
@@ -39,6 +41,9 @@ def main():
         d2.backward(g1)
         dd = disp.detach().requires_grad_(True)
         loss, _ = ops.reproj_loss(pL, pR, dd, mask, ps=PS)
+        loss.backward()
+        dd.grad = None
+        loss, _ = ops.reproj_loss(pL, pR, dd, mask, ps=PS, want_warped=True)  # loss + Fold image in one pass
         loss.backward()
         ops.reproj_loss(pL, pR, dd.detach(), mask, ps=1, want_warped=True)
         ops.patch_fold(pR, dd.detach(), PS)
