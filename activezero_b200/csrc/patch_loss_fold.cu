@@ -537,14 +537,21 @@ static int plf_launch(PlfArgs a, int B, int* nbands_out, cudaStream_t st) {
                           (grad ? (size_t)2 * (G - 1) * a.npass * 128 : 0);
     const size_t smem = floats * sizeof(float);
     if (smem > 232448 - 1024) return AZ_ERR_BAD_ARG;
-    // band size: one CTA per SM; minimise waves x (rows per band + fixed per-band cost)
+    // band size: minimise waves x (rows per band + fixed per-band cost); a wave is every SM filled with as many
+    // CTAs as its shared memory, registers (96 per thread) and thread slots allow (one at 544x960)
+    const int threads = 32 * G * a.npass;
+    int per_sm = (int)(232448 / (smem + 1024));
+    if (per_sm > 65536 / (96 * threads)) per_sm = 65536 / (96 * threads);
+    if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t slots = (int64_t)kNumSMs * per_sm;
     int best_nb = 1;
     double best = 1e30;
     for (int nb = 1; nb <= H; ++nb) {
         const int rows = (H + nb - 1) / nb;
         if (nb > 1 && rows < 2 * T::P) break;  // every full band >= 2p rows: a Fold row is shared by at most two bands
         const int nb_eff = (H + rows - 1) / rows;
-        const double waves = (double)(((int64_t)B * nb_eff + kNumSMs - 1) / kNumSMs);
+        const double waves = (double)(((int64_t)B * nb_eff + slots - 1) / slots);
         const double cost = waves * (rows + 3.0);
         if (cost < best - 1e-9) { best = cost; best_nb = nb_eff; }
         if (rows <= 4) break;
@@ -554,7 +561,6 @@ static int plf_launch(PlfArgs a, int B, int* nbands_out, cudaStream_t st) {
     if (nbands > 65535) return AZ_ERR_BAD_ARG;
     *nbands_out = nbands;
     dim3 grid((unsigned)nbands, (unsigned)B);
-    const int threads = 32 * G * a.npass;
     cudaError_t e;
     if (grad) {
         e = cudaFuncSetAttribute(patch_loss_fold_v2_kernel<PS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
