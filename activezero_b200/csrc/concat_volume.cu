@@ -1,12 +1,12 @@
 // Concat cost volume, forward and backward.
 // Reference: /root/reference/nets/psmnet/psmnet.py:151-165 (= psmnet_3.py:149-163).
 //
-// Forward is a pure store stream (2C*Dq*H*W floats out for 2*C*H*W floats in): each CTA
-// owns a contiguous run of one (b, channel) feature plane, stages it once (left half: in
-// registers; right half: in shared memory as four copies pre-shifted by 0..3 columns behind a
-// zero prefix, so that every disparity shift is an ALIGNED 128-bit shared load), and then
-// sweeps the Dq disparity planes with coalesced, streaming 128-bit stores.  Each right-feature
-// row is read from HBM exactly once per sweep.
+// Forward is a pure store stream (2C*Dq*H*W floats out for 2*C*H*W floats in): a CTA owns a
+// contiguous 8 KB run of one (b, channel) feature plane and writes it to eight consecutive
+// disparity planes with coalesced, streaming 128-bit stores (left half: the float4 stays in
+// registers; right half: the shifted row is the static window of two aligned quads read from the
+// L2-resident feature plane).  Short-lived CTAs keep the store stream closer to the write-only
+// ceiling of the part (7.5 TB/s = memset; the copy-measured "peak" of 6.5 TB/s is a read+write mix).
 //
 // Backward is a pure load stream: one thread per float4 of gL / gR walks the Dq disparity planes
 // with 8 independent 128-bit streaming loads in flight (left half: straight down; right half:
@@ -21,19 +21,40 @@ namespace az {
 
 constexpr int kFwdThreads = 256;
 constexpr int kFwdPPT = 2;  // float4 positions per thread
+constexpr int kFwdDG = 8;   // disparity planes per CTA (multiple of 4)
+
+// window [k, k+4) of the 8 floats (a, b), k in 1..4 static after unrolling
+__device__ __forceinline__ float4 cwin8(const float4& a, const float4& b, int k) {
+    switch (k) {
+        case 1: return make_float4(a.y, a.z, a.w, b.x);
+        case 2: return make_float4(a.z, a.w, b.x, b.y);
+        case 3: return make_float4(a.w, b.x, b.y, b.z);
+        default: return b;
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // forward, vectorised (W % 4 == 0, 16-byte aligned bases)
-// grid = (ceil(H*W/4 / (256*PPT)), 2C, B)
+// grid = (ceil(H*W/4 / (256*PPT)), 2C * ceil(Dq/kFwdDG), B): a CTA owns 512 consecutive float4 (8 KB) of one
+// (b, channel) feature plane and writes them to kFwdDG consecutive disparity planes.  Short-lived CTAs
+// matter: a pure store stream with this pattern reaches 7.0 TB/s when a CTA sweeps all 48 planes and
+// 7.5 TB/s (= memset) with 8 planes per CTA (benchmarks/micro/store_patterns.cu); the first version of this
+// kernel swept all planes from four pre-shifted shared-memory copies of the rows (0.515 ms at B=8 against
+// 0.490 ms for this form).
+// Left half: the float4 stays in registers, only the x >= i mask changes.
+// Right half: out[i][x..x+3] = R[x-i .. x-i+3] (0 left of the row).  The shift by i = 4m + r is the window
+// [4-r, 8-r) of two ALIGNED quads, A at x-4m-4 and B at x-4m, read straight from the feature plane (4 MB per
+// pair, L2 resident; a quad is wholly inside or wholly left of its row); B of step m+1 is A of step m, so a
+// thread issues three 128-bit loads for its eight planes and selects the windows with static register indices.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFwdThreads) concat_fwd_vec4_kernel(const float* __restrict__ L,
                                                                      const float* __restrict__ R,
                                                                      float* __restrict__ vol, int C, int H,
-                                                                     int W, int Dq, int pad, int rows_cap) {
-    extern __shared__ __align__(16) float smem[];
+                                                                     int W, int Dq, int ngroups) {
     const int W4 = W >> 2;
     const int P = kFwdThreads * kFwdPPT;
-    const int oc = blockIdx.y, b = blockIdx.z;
+    const int oc = blockIdx.y / ngroups, dg = blockIdx.y - oc * ngroups, b = blockIdx.z;
+    const int i0 = dg * kFwdDG, i1 = min(Dq, i0 + kFwdDG);
     const bool right = oc >= C;
     const int c = right ? oc - C : oc;
     const int p0 = blockIdx.x * P;
@@ -41,75 +62,37 @@ __global__ void __launch_bounds__(kFwdThreads) concat_fwd_vec4_kernel(const floa
     const size_t HW = (size_t)H * W;
     const float* src = (right ? R : L) + ((size_t)b * C + c) * HW;
     float* out = vol + ((size_t)b * 2 * C + oc) * Dq * HW;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    if (!right) {
-        // left half: value is disparity-independent, only the x >= i mask changes.
-        float4 v[kFwdPPT];
-        int x[kFwdPPT];
-        size_t off[kFwdPPT];
-        bool on[kFwdPPT];
-#pragma unroll
-        for (int k = 0; k < kFwdPPT; ++k) {
-            const int p = p0 + threadIdx.x + k * kFwdThreads;
-            on[k] = p < pend;
-            const int pp = on[k] ? p : p0;
-            off[k] = (size_t)pp * 4;
-            x[k] = (pp % W4) * 4;
-            v[k] = __ldg(reinterpret_cast<const float4*>(src + off[k]));
-        }
-        for (int i = 0; i < Dq; ++i) {
-#pragma unroll
-            for (int k = 0; k < kFwdPPT; ++k) {
-                float4 o = v[k];
-                if (x[k] + 3 < i) { o = make_float4(0.f, 0.f, 0.f, 0.f); }
-                else if (x[k] < i) {
-                    if (x[k] + 0 < i) o.x = 0.f;
-                    if (x[k] + 1 < i) o.y = 0.f;
-                    if (x[k] + 2 < i) o.z = 0.f;
-                }
-                if (on[k]) st_stream(reinterpret_cast<float4*>(out + (size_t)i * HW + off[k]), o);
-            }
-        }
-        return;
-    }
-
-    // right half: rows y_first..y_last of the plane, four pre-shifted copies each.
-    const int y_first = p0 / W4;
-    const int y_last = (pend - 1) / W4;
-    const int nrows = y_last - y_first + 1;
-    const int S = pad + W;                        // row stride (floats), multiple of 4
-    const int copy_stride = rows_cap * S;         // floats per shifted copy
-    // zero everything (prefixes + tails), then scatter the four shifted copies
-    for (int t = threadIdx.x; t < copy_stride; t += kFwdThreads)
-        reinterpret_cast<float4*>(smem)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    for (int t = threadIdx.x; t < nrows * W; t += kFwdThreads) {
-        const int y = t / W, xx = t - y * W;
-        const float val = __ldg(src + (size_t)(y_first + y) * W + xx);
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-            if (xx + r < W) smem[r * copy_stride + y * S + pad + xx + r] = val;
-    }
-    __syncthreads();
-
-    const float* sp[kFwdPPT];
-    size_t off[kFwdPPT];
-    bool on[kFwdPPT];
 #pragma unroll
     for (int k = 0; k < kFwdPPT; ++k) {
         const int p = p0 + threadIdx.x + k * kFwdThreads;
-        on[k] = p < pend;
-        const int pp = on[k] ? p : p0;
-        const int y = pp / W4, x = (pp - y * W4) * 4;
-        off[k] = (size_t)pp * 4;
-        sp[k] = smem + (y - y_first) * S + pad + x;
-    }
-    for (int i = 0; i < Dq; ++i) {
-        const int r = i & 3, k4 = i & ~3;
+        if (p >= pend) continue;
+        const int x = (p % W4) * 4;
+        const float* sp = src + (size_t)p * 4;  // feature[y][x]
+        float* op = out + (size_t)p * 4;
+        if (!right) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(sp));
+            for (int i = i0; i < i1; ++i) {
+                float4 o = v;
+                if (x + 3 < i) { o = zero; }
+                else if (x < i) {
+                    if (x + 0 < i) o.x = 0.f;
+                    if (x + 1 < i) o.y = 0.f;
+                    if (x + 2 < i) o.z = 0.f;
+                }
+                st_stream(reinterpret_cast<float4*>(op + (size_t)i * HW), o);
+            }
+        } else {
+            float4 Bv = (x - i0 >= 0) ? __ldg(reinterpret_cast<const float4*>(sp - i0)) : zero;
+            for (int m4 = i0; m4 < i1; m4 += 4) {
+                const float4 Av = (x - m4 - 4 >= 0) ? __ldg(reinterpret_cast<const float4*>(sp - m4 - 4)) : zero;
 #pragma unroll
-        for (int k = 0; k < kFwdPPT; ++k) {
-            const float4 o = *reinterpret_cast<const float4*>(sp[k] + r * copy_stride - k4);
-            if (on[k]) st_stream(reinterpret_cast<float4*>(out + (size_t)i * HW + off[k]), o);
+                for (int r = 0; r < 4; ++r)
+                    if (m4 + r < i1)
+                        st_stream(reinterpret_cast<float4*>(op + (size_t)(m4 + r) * HW), cwin8(Av, Bv, 4 - r));
+                Bv = Av;
+            }
         }
     }
 }
@@ -247,18 +230,20 @@ __global__ void __launch_bounds__(256) concat_bwd_scalar_kernel(const float* __r
 // diagonal), fixed order, atomic-free; the sums are transposed through shared memory so that gL / gR
 // are written as coalesced rows.
 // ------------------------------------------------------------------------------------------
-constexpr int kClTX = 64, kClTXB = 32, kClThreads = 256;  // positions per CTA: forward (8-16 KB store runs) / backward
+constexpr int kClTX = 64, kClTXB = 32, kClDG = 8, kClThreads = 256;  // positions per CTA (forward / backward), planes per forward CTA
 
 __global__ void __launch_bounds__(kClThreads) concat_fwd_ndhwc_kernel(const float* __restrict__ L,
                                                                     const float* __restrict__ R,
                                                                     float* __restrict__ vol, int C, int H, int W,
-                                                                    int Dq) {
+                                                                    int Dq, int ntiles) {
     extern __shared__ __align__(16) float smem[];
     const int P = C + 4;  // pitch of one position (floats): multiple of 4, not of 32
     float* LsT = smem;                // [kClTX][P]
-    float* RsT = smem + kClTX * P;    // [kClTX + Dq - 1][P]: x0 - (Dq-1) .. x0 + kClTX - 1
-    const int x0 = blockIdx.x * kClTX, y = blockIdx.y, b = blockIdx.z;
-    const int nr = kClTX + Dq - 1;
+    float* RsT = smem + kClTX * P;    // [kClTX + kClDG - 1][P]: x0 - (i1-1) .. x0 + kClTX - 1
+    const int tile = blockIdx.x % ntiles, dg = blockIdx.x / ntiles;  // short-lived CTAs: kClDG planes each
+    const int i0 = dg * kClDG, i1 = min(Dq, i0 + kClDG);
+    const int x0 = tile * kClTX, y = blockIdx.y, b = blockIdx.z;
+    const int nr = kClTX + (i1 - i0) - 1;
     const size_t HW = (size_t)H * W;
     const float* Lb = L + (size_t)b * C * HW + (size_t)y * W;
     const float* Rb = R + (size_t)b * C * HW + (size_t)y * W;
@@ -267,7 +252,7 @@ __global__ void __launch_bounds__(kClThreads) concat_fwd_ndhwc_kernel(const floa
         LsT[xl * P + c] = x < W ? __ldg(Lb + (size_t)c * HW + x) : 0.f;
     }
     for (int t = threadIdx.x; t < C * nr; t += kClThreads) {
-        const int c = t / nr, r = t - c * nr, x = x0 - (Dq - 1) + r;
+        const int c = t / nr, r = t - c * nr, x = x0 - (i1 - 1) + r;
         RsT[r * P + c] = (x >= 0 && x < W) ? __ldg(Rb + (size_t)c * HW + x) : 0.f;
     }
     __syncthreads();
@@ -278,7 +263,7 @@ __global__ void __launch_bounds__(kClThreads) concat_fwd_ndhwc_kernel(const floa
     const size_t dstep = (size_t)H * W * (2 * C);
     if (Q <= kClThreads && (kClThreads % Q) == 0 && kClTX * Q <= 4 * kClThreads &&
         ((kClThreads / Q) >= kClTX || (kClTX % (kClThreads / Q)) == 0)) {
-        // fast path (C = 4, 8, 16, 32, 64, 128): a thread keeps its channel quad q and walks <= 4 positions,
+        // fast path (C = 4, 8, 16, 32, 64): a thread keeps its channel quad q and walks <= 4 positions,
         // no integer division in the sweep; the left-half value does not depend on d and stays in registers
         const int q = threadIdx.x % Q, xstep = kClThreads / Q, nk = xstep >= kClTX ? 1 : kClTX / xstep;
         const bool left = q < C4;
@@ -293,10 +278,10 @@ __global__ void __launch_bounds__(kClThreads) concat_fwd_ndhwc_kernel(const floa
             rp[k] = RsT;
             if (xs[k] >= 0) {
                 if (left) vl[k] = *reinterpret_cast<const float4*>(LsT + xl * P + 4 * q);
-                else rp[k] = RsT + (xl + Dq - 1) * P + 4 * (q - C4);
+                else rp[k] = RsT + (xl + i1 - 1) * P + 4 * (q - C4);
             }
         }
-        for (int d = 0; d < Dq; ++d) {
+        for (int d = i0; d < i1; ++d) {
             float4* od = reinterpret_cast<float4*>(vrow + (size_t)d * dstep) + threadIdx.x;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -309,14 +294,14 @@ __global__ void __launch_bounds__(kClThreads) concat_fwd_ndhwc_kernel(const floa
         }
         return;
     }
-    for (int d = 0; d < Dq; ++d) {
+    for (int d = i0; d < i1; ++d) {
         float4* od = reinterpret_cast<float4*>(vrow + (size_t)d * dstep);
         for (int t = threadIdx.x; t < npos * Q; t += kClThreads) {
             const int xl = t / Q, q = t - xl * Q;
             float4 v = zero;
             if (x0 + xl >= d)
                 v = q < C4 ? *reinterpret_cast<const float4*>(LsT + xl * P + 4 * q)
-                           : *reinterpret_cast<const float4*>(RsT + (xl - d + Dq - 1) * P + 4 * (q - C4));
+                           : *reinterpret_cast<const float4*>(RsT + (xl - d + i1 - 1) * P + 4 * (q - C4));
             st_stream(od + t, v);
         }
     }
@@ -383,22 +368,14 @@ extern "C" int az_concat_volume_fwd(const float* L, const float* R, float* vol, 
     if (vec) {
         const int W4 = (int)(W / 4);
         const int P = kFwdThreads * kFwdPPT;
-        const int pad = (int)((Dq + 3) / 4 * 4);
-        const int rows_cap = (P + W4 - 1) / W4 + 1;
-        const size_t smem = (size_t)4 * rows_cap * (pad + W) * sizeof(float);
-        if (smem <= 200 * 1024) {
-            // per launch, not cached: the attribute is per device and the call costs ~1 us
-            cudaError_t e = cudaFuncSetAttribute(concat_fwd_vec4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 200 * 1024);
-            if (e != cudaSuccess) return (int)e;
-            dim3 grid((unsigned)ceil_div(H * W4, P), (unsigned)(2 * C), (unsigned)B);
-            concat_fwd_vec4_kernel<<<grid, kFwdThreads, smem, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq, pad,
-                                                                   rows_cap);
+        const int64_t ngroups = ceil_div(Dq, kFwdDG);
+        if (2 * C * ngroups <= 65535) {
+            dim3 grid((unsigned)ceil_div(H * W4, P), (unsigned)(2 * C * ngroups), (unsigned)B);
+            concat_fwd_vec4_kernel<<<grid, kFwdThreads, 0, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq, (int)ngroups);
             AZ_LAUNCH_CHECK();
             return 0;
         }
     }
-    if (Dq > 65535 || B * 2 * C > 65535) return AZ_ERR_BAD_ARG;
     dim3 grid((unsigned)ceil_div(H * W, 256), (unsigned)Dq, (unsigned)(B * 2 * C));
     concat_fwd_scalar_kernel<<<grid, 256, 0, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq);
     AZ_LAUNCH_CHECK();
@@ -428,12 +405,15 @@ extern "C" int az_concat_volume_fwd_ndhwc(const float* L, const float* R, float*
                                           int64_t W, int64_t Dq, void* stream) {
     if (!L || !R || !vol || B <= 0 || C <= 0 || H <= 0 || W <= 0 || Dq <= 0) return AZ_ERR_BAD_ARG;
     if ((C % 4) != 0 || !aligned16(vol) || B > 65535 || H > 65535 || H * W >= (1ll << 31) / 4) return AZ_ERR_BAD_ARG;
-    const size_t smem = (size_t)(2 * kClTX + Dq - 1) * (size_t)(C + 4) * sizeof(float);
+    const size_t smem = (size_t)(2 * kClTX + kClDG - 1) * (size_t)(C + 4) * sizeof(float);
     if (smem > 200 * 1024) return AZ_ERR_BAD_ARG;
+    const int64_t ntiles = ceil_div(W, kClTX), ngroups = ceil_div(Dq, kClDG);
+    if (ntiles * ngroups >= (1ll << 31)) return AZ_ERR_BAD_ARG;
     cudaError_t e = cudaFuncSetAttribute(concat_fwd_ndhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid((unsigned)ceil_div(W, kClTX), (unsigned)H, (unsigned)B);
-    concat_fwd_ndhwc_kernel<<<grid, kClThreads, smem, (cudaStream_t)stream>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq);
+    dim3 grid((unsigned)(ntiles * ngroups), (unsigned)H, (unsigned)B);
+    concat_fwd_ndhwc_kernel<<<grid, kClThreads, smem, (cudaStream_t)stream>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq,
+                                                                              (int)ntiles);
     AZ_LAUNCH_CHECK();
     return 0;
 }
