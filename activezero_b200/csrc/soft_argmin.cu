@@ -16,6 +16,7 @@ namespace az {
 
 constexpr int kSAThreads = 256;
 constexpr int kChunk = 8;
+constexpr int kBwdDGroup = 16;  // planes per backward CTA (multiple of kChunk)
 constexpr float kLog2e = 1.4426950408889634f;
 
 template <int V> struct Vec;
@@ -110,7 +111,9 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_bwd_kernel(const float
                                                                     const float* __restrict__ lse,
                                                                     const float* __restrict__ gdisp,
                                                                     float* __restrict__ gcost, int D,
-                                                                    int64_t plane, int64_t n_vec) {
+                                                                    int64_t plane, int64_t n_vec, int dgroup) {
+    // grid.y splits the D planes into groups of `dgroup`: short-lived CTAs keep the store half of this
+    // read-modify-write stream nearer the write-only ceiling (benchmarks/micro/store_patterns.cu)
     using VT = typename Vec<V>::T;
     const int64_t t = (int64_t)blockIdx.x * kSAThreads + threadIdx.x;
     if (t >= n_vec) return;
@@ -118,19 +121,20 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_bwd_kernel(const float
     const int64_t b = pix / plane, hw = pix - b * plane;
     const float* src = cost + b * D * plane + hw;
     float* dst = gcost + b * D * plane + hw;
+    const int dbeg = blockIdx.y * dgroup, dend = min(D, dbeg + dgroup);
     float o[V], mx[V], lb[V], g[V];
     Vec<V>::unpack(*reinterpret_cast<const VT*>(disp + pix), o);
     Vec<V>::unpack(*reinterpret_cast<const VT*>(lse + pix), mx);
     Vec<V>::unpack(*reinterpret_cast<const VT*>(lse + n_vec * V + pix), lb);
     Vec<V>::unpack(*reinterpret_cast<const VT*>(gdisp + pix), g);
-    for (int d0 = 0; d0 < D; d0 += kChunk) {
+    for (int d0 = dbeg; d0 < dend; d0 += kChunk) {
         VT v[kChunk];
 #pragma unroll
         for (int k = 0; k < kChunk; ++k)
-            if (d0 + k < D) v[k] = ld_stream(reinterpret_cast<const VT*>(src + (int64_t)(d0 + k) * plane));
+            if (d0 + k < dend) v[k] = ld_stream(reinterpret_cast<const VT*>(src + (int64_t)(d0 + k) * plane));
 #pragma unroll
         for (int k = 0; k < kChunk; ++k) {
-            if (d0 + k < D) {
+            if (d0 + k < dend) {
                 float x[V], r[V];
                 Vec<V>::unpack(v[k], x);
                 const float dd = (float)(d0 + k);
@@ -174,13 +178,17 @@ extern "C" int az_soft_argmin_bwd(const float* cost, const float* disp, const fl
     const int64_t plane = H * W, total = B * plane;
     const bool vec = (plane % 4 == 0) && aligned16(cost) && aligned16(disp) && aligned16(lse) && aligned16(gdisp) &&
                      aligned16(gcost);
+    const int dgroup = kBwdDGroup;
+    const unsigned ngroups = (unsigned)ceil_div(D, dgroup);
+    if (ngroups > 65535) return AZ_ERR_BAD_ARG;
     if (vec) {
         const int64_t n = total / 4;
-        soft_argmin_bwd_kernel<4><<<(unsigned)ceil_div(n, kSAThreads), kSAThreads, 0, st>>>(cost, disp, lse, gdisp,
-                                                                                           gcost, (int)D, plane, n);
+        dim3 grid((unsigned)ceil_div(n, kSAThreads), ngroups);
+        soft_argmin_bwd_kernel<4><<<grid, kSAThreads, 0, st>>>(cost, disp, lse, gdisp, gcost, (int)D, plane, n, dgroup);
     } else {
-        soft_argmin_bwd_kernel<1><<<(unsigned)ceil_div(total, kSAThreads), kSAThreads, 0, st>>>(
-            cost, disp, lse, gdisp, gcost, (int)D, plane, total);
+        dim3 grid((unsigned)ceil_div(total, kSAThreads), ngroups);
+        soft_argmin_bwd_kernel<1><<<grid, kSAThreads, 0, st>>>(cost, disp, lse, gdisp, gcost, (int)D, plane, total,
+                                                               dgroup);
     }
     AZ_LAUNCH_CHECK();
     return 0;
