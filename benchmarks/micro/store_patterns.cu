@@ -45,6 +45,25 @@ template <bool CS, int DG> __global__ void __launch_bounds__(256) k_plane_dgroup
         }
 }
 
+// (5) as (4) with the value LOADED first from a small L2-resident plane (what the concat kernel does): how much
+// does the load -> store dependency of a short-lived CTA cost?
+template <int DG> __global__ void __launch_bounds__(256) k_plane_dgroup_ld(const float4* __restrict__ feat, float4* out) {
+    const long long base = (long long)blockIdx.z * DQ * PLANE4 + (long long)blockIdx.y * DG * PLANE4;
+    const int p0 = blockIdx.x * 512;
+    float4 v[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int p = p0 + k * 256 + threadIdx.x;
+        v[k] = p < PLANE4 ? __ldg(feat + (long long)(blockIdx.z % 64) * PLANE4 + p) : make_float4(0, 0, 0, 0);
+    }
+    for (int d = 0; d < DG; ++d)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int p = p0 + k * 256 + threadIdx.x;
+            if (p < PLANE4) __stcs(out + base + (long long)d * PLANE4 + p, v[k]);
+        }
+}
+
 template <class F> float timeit(F f) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     for (int i = 0; i < 3; ++i) f();
@@ -73,6 +92,10 @@ int main() {
     rep("plane sweep, 8 planes per CTA, .cs", timeit([&] { k_plane_dgroup<true, 8><<<dim3(16, 6, NOC * NB), 256>>>(out, v); }));
     rep("plane sweep, 1 plane per CTA, .cs", timeit([&] { k_plane_dgroup<true, 1><<<dim3(16, 48, NOC * NB), 256>>>(out, v); }));
     rep("plane sweep, 1 plane per CTA, default", timeit([&] { k_plane_dgroup<false, 1><<<dim3(16, 48, NOC * NB), 256>>>(out, v); }));
+    float4* feat; cudaMalloc(&feat, 64 * PLANE4 * 16); cudaMemset(feat, 0, 64 * PLANE4 * 16);
+    rep("plane sweep, 8 planes per CTA, loaded value", timeit([&] { k_plane_dgroup_ld<8><<<dim3(16, 6, NOC * NB), 256>>>(feat, out); }));
+    rep("plane sweep, 16 planes per CTA, loaded value", timeit([&] { k_plane_dgroup_ld<16><<<dim3(16, 3, NOC * NB), 256>>>(feat, out); }));
+    rep("plane sweep, 48 planes per CTA, loaded value", timeit([&] { k_plane_dgroup_ld<48><<<dim3(16, 1, NOC * NB), 256>>>(feat, out); }));
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
