@@ -527,7 +527,10 @@ static int plf_launch(PlfArgs a, int B, int* nbands_out, cudaStream_t st) {
     if (G > 3) G = 3;
     if (G > T::NP) G = T::NP;
     a.G = G;
-    a.pitchR = (T::OFF_R + W + T::P + 1 + 3) & ~3;
+    // plane stride (pitchR / 4 slots of 8 bytes) a multiple of 16 slots = 128 bytes: the bank of element xx is then
+    // (xx >> 2) mod 16 whatever its plane, so two lanes of a half-warp only collide when their window starts fall
+    // into the same aligned group of four columns -- one disparity step in four instead of (almost) every step
+    a.pitchR = (T::OFF_R + W + T::P + 1 + 63) & ~63;
     a.pitchL = (W + 3 * T::P + 4 + 3) & ~3;
     a.pitchV = (W + 3) & ~3;
     a.pitchP = (a.npass - 1) * T::S + 128;
