@@ -2,7 +2,7 @@
 // Reference: /root/reference/nets/psmnet/psmnet.py:151-165 (= psmnet_3.py:149-163).
 //
 // Forward is a pure store stream (2C*Dq*H*W floats out for 2*C*H*W floats in): a CTA owns a
-// contiguous 8 KB run of one (b, channel) feature plane and writes it to eight consecutive
+// contiguous 4 KB run of one (b, channel) feature plane and writes it to eight consecutive
 // disparity planes with coalesced, streaming 128-bit stores (left half: the float4 stays in
 // registers; right half: the shifted row is the static window of two aligned quads read from the
 // L2-resident feature plane).  Short-lived CTAs keep the store stream closer to the write-only
@@ -20,7 +20,7 @@
 namespace az {
 
 constexpr int kFwdThreads = 256;
-constexpr int kFwdPPT = 2;  // float4 positions per thread
+constexpr int kFwdPPT = 1;  // float4 positions per thread
 constexpr int kFwdDG = 8;   // disparity planes per CTA (multiple of 4)
 
 // window [k, k+4) of the 8 floats (a, b), k in 1..4 static after unrolling
@@ -35,12 +35,12 @@ __device__ __forceinline__ float4 cwin8(const float4& a, const float4& b, int k)
 
 // ------------------------------------------------------------------------------------------
 // forward, vectorised (W % 4 == 0, 16-byte aligned bases)
-// grid = (ceil(H*W/4 / (256*PPT)), 2C * ceil(Dq/kFwdDG), B): a CTA owns 512 consecutive float4 (8 KB) of one
+// grid = (ceil(H*W/4 / (256*PPT)), 2C * ceil(Dq/kFwdDG), B): a CTA owns 256 consecutive float4 (4 KB) of one
 // (b, channel) feature plane and writes them to kFwdDG consecutive disparity planes.  Short-lived CTAs
 // matter: a pure store stream with this pattern reaches 7.0 TB/s when a CTA sweeps all 48 planes and
 // 7.5 TB/s (= memset) with 8 planes per CTA (benchmarks/micro/store_patterns.cu); the first version of this
-// kernel swept all planes from four pre-shifted shared-memory copies of the rows (0.515 ms at B=8 against
-// 0.490 ms for this form).
+// kernel swept all planes in 8 KB runs from four pre-shifted shared-memory copies of the rows (0.515 ms at
+// B=8 against 0.488 ms for this form; 8 KB runs with 8 planes per CTA: 0.495 ms, 16 planes: 0.498 ms).
 // Left half: the float4 stays in registers, only the x >= i mask changes.
 // Right half: out[i][x..x+3] = R[x-i .. x-i+3] (0 left of the row).  The shift by i = 4m + r is the window
 // [4-r, 8-r) of two ALIGNED quads, A at x-4m-4 and B at x-4m, read straight from the feature plane (4 MB per
