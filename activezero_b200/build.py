@@ -37,11 +37,27 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every csrc/*.cu to an object (in parallel, only the stale ones unless `force`) and link."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", LIB_PATH]
-    subprocess.check_call(cmd)
+    obj_dir = os.path.join(PKG_DIR, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(os.path.dirname(PKG_DIR), "include", "*.h"))
+    hdr_t = max(os.path.getmtime(h) for h in hdrs)
+    flags = [f for f in NVCC_FLAGS if f not in ("-shared", "-cudart", "static")]
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append([nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        list(ex.map(subprocess.check_call, jobs))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
+                          + objs + ["-o", LIB_PATH])
     return LIB_PATH
 
 

@@ -97,6 +97,90 @@ __global__ void __launch_bounds__(kFwdThreads) concat_fwd_vec4_kernel(const floa
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// forward through the bulk-store engine (round 2, north-star "TMA bulk copies"): the output never
+// crosses the register file.  The LSU only stages the input rows in shared memory (1/48 + 4/48 of the
+// output bytes); every output byte is written by cp.async.bulk shared -> global (SASS UBLKCP).
+//   right half: out[C+c][i][y][:] = R[y][: - i].  Four copies of each row, pre-shifted by r = 0..3 floats
+//     behind a zero prefix of PAD >= Dq floats, make the source of plane i = 4m + r the 16-byte aligned
+//     address copy_r[y] + PAD - 4m: one 4*W-byte bulk copy per (plane, row), no waits (the staged rows are
+//     never modified).
+//   left half:  out[c][i][y][:] = L[y][:] with the first i columns zeroed.  The rows are staged densely
+//     (pitch W), so an 8-row chunk of a plane is ONE contiguous copy on both sides; the thread that owns a
+//     chunk walks the planes in order and zeroes column i-1 in place before plane i
+//     (cp.async.bulk.wait_group.read, 8 stores, fence.proxy.async, next copy).
+// grid = (nL + nR, C, B): blockIdx.x < nL -> left CTA of kBulkRowsL rows, else right CTA of kBulkRowsR rows.
+// ------------------------------------------------------------------------------------------
+constexpr int kBulkThreads = 128, kBulkRowsL = 32, kBulkChunk = 8, kBulkRowsR = 8;
+
+__global__ void __launch_bounds__(kBulkThreads) concat_fwd_bulk_kernel(const float* __restrict__ L,
+                                                                       const float* __restrict__ R,
+                                                                       float* __restrict__ vol, int C, int H, int W,
+                                                                       int Dq, int nL, int PAD, int halves) {
+    extern __shared__ __align__(128) float sm[];
+    const int tid = threadIdx.x;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const size_t HW = (size_t)H * W;
+    const int W4 = W >> 2;
+    if ((int)blockIdx.x < nL) {
+        if (!(halves & 1)) return;
+        const int y0 = blockIdx.x * kBulkRowsL, nrows = min(kBulkRowsL, H - y0);
+        const float* src = L + ((size_t)b * C + c) * HW + (size_t)y0 * W;
+        for (int t = tid; t < nrows * W4; t += kBulkThreads)
+            reinterpret_cast<float4*>(sm)[t] = __ldg(reinterpret_cast<const float4*>(src) + t);
+        fence_async_smem();
+        __syncthreads();
+        const int nchunks = (nrows + kBulkChunk - 1) / kBulkChunk;
+        if (tid < nchunks) {
+            const int r0 = tid * kBulkChunk, nr = min(kBulkChunk, nrows - r0);
+            float* chunk = sm + (size_t)r0 * W;
+            float* out = vol + ((size_t)b * 2 * C + c) * Dq * HW + (size_t)(y0 + r0) * W;
+            const uint32_t bytes = (uint32_t)(nr * W) * 4u;
+            for (int i = 0; i < Dq; ++i) {
+                if (i > 0 && i <= W) {
+                    bulk_wait_read<0>();  // plane i-1 has been read out of shared memory
+                    for (int r = 0; r < nr; ++r) chunk[r * W + i - 1] = 0.f;
+                    fence_async_smem();
+                }
+                bulk_s2g(out + (size_t)i * HW, chunk, bytes);
+                bulk_commit();
+            }
+            bulk_wait_read<0>();
+        }
+    } else {
+        if (!(halves & 2)) return;
+        const int y0 = ((int)blockIdx.x - nL) * kBulkRowsR, nrows = min(kBulkRowsR, H - y0);
+        const int PW = PAD + W;                       // row pitch of a staged copy (multiple of 4)
+        const float* src = R + ((size_t)b * C + c) * HW + (size_t)y0 * W;
+        // copy r, row y: [zeros(PAD + r) | R[y][0 .. W - r)]
+        const int PW4 = PW >> 2, PAD4 = PAD >> 2;
+        for (int t = tid; t < nrows * PW4; t += kBulkThreads) {
+            const int y = t / PW4, q = t - y * PW4;   // quad q of the padded row
+            float4 cur = make_float4(0.f, 0.f, 0.f, 0.f), prev = cur;
+            if (q >= PAD4) cur = __ldg(reinterpret_cast<const float4*>(src + (size_t)y * W) + (q - PAD4));
+            if (q > PAD4) prev = __ldg(reinterpret_cast<const float4*>(src + (size_t)y * W) + (q - PAD4 - 1));
+            float* d = sm + (size_t)y * PW + 4 * q;
+            const size_t cs = (size_t)kBulkRowsR * PW;  // floats per copy
+            *reinterpret_cast<float4*>(d) = cur;
+            *reinterpret_cast<float4*>(d + cs) = make_float4(prev.w, cur.x, cur.y, cur.z);
+            *reinterpret_cast<float4*>(d + 2 * cs) = make_float4(prev.z, prev.w, cur.x, cur.y);
+            *reinterpret_cast<float4*>(d + 3 * cs) = make_float4(prev.y, prev.z, prev.w, cur.x);
+        }
+        fence_async_smem();
+        __syncthreads();
+        float* out = vol + ((size_t)b * 2 * C + C + c) * Dq * HW + (size_t)y0 * W;
+        const uint32_t bytes = (uint32_t)W * 4u;
+        for (int idx = tid; idx < Dq * nrows; idx += kBulkThreads) {
+            const int i = idx / nrows, y = idx - i * nrows;
+            const float* s = sm + (size_t)(i & 3) * kBulkRowsR * PW + (size_t)y * PW + PAD - (i & ~3);
+            bulk_s2g(out + (size_t)i * HW + (size_t)y * W, s, bytes);
+        }
+        bulk_commit();
+        bulk_wait_read<0>();
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // forward, scalar fallback (any W, any alignment): one thread per output element of a
 // (b, oc, i) plane.  grid = (ceil(H*W/256), Dq, B*2C)
@@ -369,6 +453,26 @@ extern "C" int az_concat_volume_fwd(const float* L, const float* R, float* vol, 
         const int W4 = (int)(W / 4);
         const int P = kFwdThreads * kFwdPPT;
         const int64_t ngroups = ceil_div(Dq, kFwdDG);
+        // 0 = register/LSU store path; 1 = both halves through the bulk-store engine; 2 = right half bulk, left half LSU
+        const int impl = tuning("AZ_CONCAT_FWD", 0);
+        const int PAD = (int)((Dq + 3) / 4 * 4);
+        const size_t smemL = (size_t)kBulkRowsL * W * 4, smemR = (size_t)4 * kBulkRowsR * (PAD + W) * 4;
+        const size_t smemB = smemL > smemR ? smemL : smemR;
+        if (impl != 0 && smemB <= 200 * 1024 && C <= 65535 && Dq <= W) {
+            const int nL = (int)ceil_div(H, kBulkRowsL), nR = (int)ceil_div(H, kBulkRowsR);
+            cudaError_t e = cudaFuncSetAttribute(concat_fwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            dim3 gb((unsigned)(nL + nR), (unsigned)C, (unsigned)B);
+            concat_fwd_bulk_kernel<<<gb, kBulkThreads, smemB, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq, nL, PAD,
+                                                                    impl == 1 ? 3 : 2);
+            AZ_LAUNCH_CHECK();
+            if (impl == 2) {  // left half: channels [0, C) of the LSU kernel
+                dim3 grid((unsigned)ceil_div(H * W4, P), (unsigned)(C * ngroups), (unsigned)B);
+                concat_fwd_vec4_kernel<<<grid, kFwdThreads, 0, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq, (int)ngroups);
+                AZ_LAUNCH_CHECK();
+            }
+            return 0;
+        }
         if (2 * C * ngroups <= 65535) {
             dim3 grid((unsigned)ceil_div(H * W4, P), (unsigned)(2 * C * ngroups), (unsigned)B);
             concat_fwd_vec4_kernel<<<grid, kFwdThreads, 0, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq, (int)ngroups);

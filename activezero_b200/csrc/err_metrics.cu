@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(kEMThreads) err_metrics_kernel(const float* __
         acc[1] += (double)dd;
         acc[2] += dd > 1.0f ? 1.0 : 0.0;
         acc[3] += dd > 2.0f ? 1.0 : 0.0;
-        acc[4] += (double)fminf(fmaxf(e1000, 0.0f), 100.0f);
+        // torch.clip propagates NaN (a diverged model must not report a finite depth error); fminf/fmaxf drop it
+        acc[4] += (e1000 != e1000) ? (double)e1000 : (double)fminf(fmaxf(e1000, 0.0f), 100.0f);
         acc[5] += zd > 2e-3f ? 1.0 : 0.0;
         acc[6] += zd > 4e-3f ? 1.0 : 0.0;
         acc[7] += zd > 8e-3f ? 1.0 : 0.0;

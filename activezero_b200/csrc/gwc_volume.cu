@@ -95,6 +95,65 @@ __global__ void __launch_bounds__(kGwcThreads) gwc_fwd_vec4_kernel(const float* 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// forward, short-lived CTAs (round 2; the kernel above swept all Dq planes per CTA and reached
+// 0.50-0.73 of the measured peak).  Same shape as the concat forward that sits at the store-stream
+// ceiling: a CTA owns 256 float4 positions of one (b, group) and writes `DG` consecutive disparity
+// planes; the left quads stay in registers, the shifted right window of plane i = 4m + r is the static
+// register window [4-r, 8-r) of two aligned quads read straight from the L2-resident feature plane
+// (B of step m+1 is A of step m).  No shared memory, no barrier.
+// grid = (ceil(H*W/4 / 256), G * ceil(Dq/DG), B)
+// ------------------------------------------------------------------------------------------
+template <int CPG>
+__global__ void __launch_bounds__(kGwcThreads) gwc_fwd_planes_kernel(const float* __restrict__ L,
+                                                                    const float* __restrict__ R,
+                                                                    float* __restrict__ vol, int C, int G, int H, int W,
+                                                                    int Dq, int DG, int ngroups) {
+    const int W4 = W >> 2;
+    const int g = blockIdx.y / ngroups, dg = blockIdx.y - g * ngroups, b = blockIdx.z;
+    const int i0 = dg * DG, i1 = min(Dq, i0 + DG);
+    const int pp = blockIdx.x * kGwcThreads + threadIdx.x;
+    if (pp >= H * W4) return;
+    const int x = (pp % W4) * 4;
+    const size_t HW = (size_t)H * W;
+    const float* Lg = L + ((size_t)b * C + (size_t)g * CPG) * HW + (size_t)pp * 4;
+    const float* Rg = R + ((size_t)b * C + (size_t)g * CPG) * HW + (size_t)pp * 4;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float inv = 1.0f / (float)CPG;
+    float4 l[CPG], Bw[CPG];
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(Lg + (size_t)c * HW));
+        l[c] = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
+        Bw[c] = (x - i0 >= 0) ? __ldg(reinterpret_cast<const float4*>(Rg + (size_t)c * HW - i0)) : zero;
+    }
+    float* out = vol + ((size_t)b * G + g) * Dq * HW + (size_t)pp * 4;
+    for (int m4 = i0; m4 < i1; m4 += 4) {
+        float4 A[CPG];
+#pragma unroll
+        for (int c = 0; c < CPG; ++c)
+            A[c] = (x - m4 - 4 >= 0) ? __ldg(reinterpret_cast<const float4*>(Rg + (size_t)c * HW - m4 - 4)) : zero;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (m4 + r < i1) {
+                float4 acc = zero;
+#pragma unroll
+                for (int c = 0; c < CPG; ++c) {
+                    const float4 w = win8(A[c], Bw[c], 4 - r);
+                    acc.x = fmaf(l[c].x, w.x, acc.x);
+                    acc.y = fmaf(l[c].y, w.y, acc.y);
+                    acc.z = fmaf(l[c].z, w.z, acc.z);
+                    acc.w = fmaf(l[c].w, w.w, acc.w);
+                }
+                st_stream(reinterpret_cast<float4*>(out + (size_t)(m4 + r) * HW), acc);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) Bw[c] = A[c];
+    }
+}
+
 // scalar fallback, any shape.  grid = (ceil(H*W/256), Dq, B*G)
 __global__ void __launch_bounds__(256) gwc_fwd_scalar_kernel(const float* __restrict__ L, const float* __restrict__ R,
                                                              float* __restrict__ vol, int C, int G, int H, int W,
@@ -222,6 +281,122 @@ __global__ void __launch_bounds__(kGwcThreads, 3) gwc_bwd_direct_kernel(const fl
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// backward, one pass over the gradient volume (round 2; the direct kernel above re-read the
+// volume once per channel pair and reached 0.33-0.45 of the measured peak).
+// One CTA owns one image row y of one (b, group): the Dq gradient rows g[i][y][:], and the CPG left /
+// right feature rows, are brought into shared memory with 1-D bulk async copies (TMA, one per row,
+// completing on an mbarrier) -- every byte of gvol crosses HBM exactly once -- and both gradients are
+// then formed from shared memory in a fixed order (gather-style, atomic-free):
+//   gL[c,x] = inv * sum_i g[i,x]   * R[c,x-i]     (R behind a zero prefix)
+//   gR[c,x] = inv * sum_i g[i,x+i] * L[c,x+i]     (g and L in front of a zero tail)
+// A thread owns one float4 of columns of one side for ALL CPG channels, so a gradient quad is read from
+// shared memory once per side.  grid = (H, G, B), 128 threads.
+// smem: Gs[Dq][GP] | Ls[CPG][GP] | Rs[CPG][pad + W];  GP = W + Dq + 8 (rounded), pad = Dq + 4 (rounded)
+// ------------------------------------------------------------------------------------------
+constexpr int kGwcRowThreads = 128;
+
+template <int CPG>
+__global__ void __launch_bounds__(kGwcRowThreads) gwc_bwd_row_kernel(const float* __restrict__ gvol,
+                                                                    const float* __restrict__ L,
+                                                                    const float* __restrict__ R,
+                                                                    float* __restrict__ gL, float* __restrict__ gR,
+                                                                    int C, int G, int H, int W, int Dq, int GP, int pad) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    float* Gs = smem;
+    float* Ls = Gs + (size_t)Dq * GP;
+    float* Rs = Ls + (size_t)CPG * GP;
+    const int RP = pad + W;
+    const int tid = threadIdx.x;
+    const int y = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+    const size_t HW = (size_t)H * W;
+    const uint32_t row_bytes = (uint32_t)W * 4u;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar, row_bytes * (uint32_t)(Dq + 2 * CPG));
+    }
+    // zero tails / prefix (disjoint from the bulk destinations)
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int tailq = (GP - W) >> 2, padq = pad >> 2;
+    for (int t = tid; t < (Dq + CPG) * tailq; t += kGwcRowThreads) {
+        const int r = t / tailq, q = t - r * tailq;
+        reinterpret_cast<float4*>(Gs + (size_t)r * GP + W)[q] = zero;  // Ls rows follow Gs with the same pitch
+    }
+    for (int t = tid; t < CPG * padq; t += kGwcRowThreads) {
+        const int r = t / padq, q = t - r * padq;
+        reinterpret_cast<float4*>(Rs + (size_t)r * RP)[q] = zero;
+    }
+    __syncthreads();
+    const float* grow = gvol + ((size_t)b * G + g) * Dq * HW + (size_t)y * W;
+    const size_t fbase = ((size_t)b * C + (size_t)g * CPG) * HW + (size_t)y * W;
+    for (int r = tid; r < Dq + 2 * CPG; r += kGwcRowThreads) {
+        if (r < Dq) bulk_g2s(Gs + (size_t)r * GP, grow + (size_t)r * HW, row_bytes, &bar);
+        else if (r < Dq + CPG) bulk_g2s(Ls + (size_t)(r - Dq) * GP, L + fbase + (size_t)(r - Dq) * HW, row_bytes, &bar);
+        else bulk_g2s(Rs + (size_t)(r - Dq - CPG) * RP + pad, R + fbase + (size_t)(r - Dq - CPG) * HW, row_bytes, &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    const int W4 = W >> 2;
+    const float inv = 1.0f / (float)CPG;
+    for (int task = tid; task < 2 * W4; task += kGwcRowThreads) {
+        const bool right = task >= W4;
+        const int x = (right ? task - W4 : task) * 4;
+        float* gout = right ? gR : gL;
+        if (gout == nullptr) continue;
+        float4 acc[CPG], A[CPG], Bq[CPG];
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) acc[c] = zero;
+        if (!right) {
+            const float* rp = Rs + pad + x;
+#pragma unroll
+            for (int c = 0; c < CPG; ++c) Bq[c] = *reinterpret_cast<const float4*>(rp + c * RP);
+            for (int m4 = 0; m4 < Dq; m4 += 4) {
+#pragma unroll
+                for (int c = 0; c < CPG; ++c) A[c] = *reinterpret_cast<const float4*>(rp + c * RP - m4 - 4);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (m4 + r < Dq) {
+                        const float4 gq = *reinterpret_cast<const float4*>(Gs + (size_t)(m4 + r) * GP + x);
+#pragma unroll
+                        for (int c = 0; c < CPG; ++c) fma4(acc[c], gq, win8(A[c], Bq[c], 4 - r));
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CPG; ++c) Bq[c] = A[c];
+            }
+        } else {
+            const float* lp = Ls + x;
+#pragma unroll
+            for (int c = 0; c < CPG; ++c) A[c] = *reinterpret_cast<const float4*>(lp + c * GP);
+            for (int m4 = 0; m4 < Dq; m4 += 4) {
+#pragma unroll
+                for (int c = 0; c < CPG; ++c) Bq[c] = *reinterpret_cast<const float4*>(lp + c * GP + m4 + 4);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (m4 + r < Dq) {
+                        const float* gp = Gs + (size_t)(m4 + r) * GP + x + m4;
+                        const float4 ga = *reinterpret_cast<const float4*>(gp);
+                        const float4 gb = *reinterpret_cast<const float4*>(gp + 4);
+                        const float4 gw = win8k(ga, gb, r);
+#pragma unroll
+                        for (int c = 0; c < CPG; ++c) fma4(acc[c], gw, win8k(A[c], Bq[c], r));
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CPG; ++c) A[c] = Bq[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CPG; ++c)
+            *reinterpret_cast<float4*>(gout + fbase + (size_t)c * HW + x) =
+                make_float4(acc[c].x * inv, acc[c].y * inv, acc[c].z * inv, acc[c].w * inv);
+    }
+}
+
 // scalar fallback: one thread per (b, c, y, x).  grid = (ceil(H*W/256), C, B)
 __global__ void __launch_bounds__(256) gwc_bwd_scalar_kernel(const float* __restrict__ gvol,
                                                              const float* __restrict__ L, const float* __restrict__ R,
@@ -248,10 +423,22 @@ __global__ void __launch_bounds__(256) gwc_bwd_scalar_kernel(const float* __rest
 template <int CPG>
 static int launch_gwc_fwd(const float* L, const float* R, float* vol, int B, int C, int G, int H, int W, int Dq,
                           cudaStream_t st, bool* done) {
-    const int W4 = W / 4, pad = (Dq + 3) / 4 * 4 + 4;
+    const int W4 = W / 4;
+    *done = false;
+    int DG = tuning("AZ_GWC_DG", 8);  // planes per CTA; 0 = round-1 kernel (all planes per CTA, rows in shared memory)
+    if (DG > 0) {
+        DG = (DG + 3) & ~3;
+        const int64_t ngroups = ceil_div(Dq, DG);
+        if ((int64_t)G * ngroups <= 65535) {
+            dim3 grid((unsigned)ceil_div((int64_t)H * W4, kGwcThreads), (unsigned)(G * ngroups), (unsigned)B);
+            gwc_fwd_planes_kernel<CPG><<<grid, kGwcThreads, 0, st>>>(L, R, vol, C, G, H, W, Dq, DG, (int)ngroups);
+            *done = true;
+            return (int)cudaGetLastError();
+        }
+    }
+    const int pad = (Dq + 3) / 4 * 4 + 4;
     const int rows_cap = (kGwcThreads + W4 - 1) / W4 + 1;
     const size_t smem = (size_t)CPG * rows_cap * (pad + W) * sizeof(float);
-    *done = false;
     if (smem > 200 * 1024) return 0;
     cudaError_t e = cudaFuncSetAttribute(gwc_fwd_vec4_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          200 * 1024);
@@ -266,10 +453,23 @@ template <int CPG>
 static int launch_gwc_bwd(const float* gvol, const float* L, const float* R, float* gL, float* gR, int B, int C, int G,
                           int H, int W, int Dq, cudaStream_t st, bool* done) {
     constexpr int CPT = CPG >= 2 ? 2 : 1;
+    *done = false;
+    if (tuning("AZ_GWC_BWD", 1) == 1 && H <= 65535) {  // one-pass row kernel (TMA bulk staging)
+        const int padr = (Dq + 3) / 4 * 4 + 4, GP = (W + Dq + 8 + 3) & ~3;
+        const size_t smem_row = ((size_t)(Dq + CPG) * GP + (size_t)CPG * (padr + W)) * sizeof(float);
+        if (smem_row <= 200 * 1024 && (size_t)(Dq + 2 * CPG) * W * 4 < (1u << 20)) {
+            cudaError_t er = cudaFuncSetAttribute(gwc_bwd_row_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  200 * 1024);
+            if (er != cudaSuccess) return (int)er;
+            dim3 grid((unsigned)H, (unsigned)G, (unsigned)B);
+            gwc_bwd_row_kernel<CPG><<<grid, kGwcRowThreads, smem_row, st>>>(gvol, L, R, gL, gR, C, G, H, W, Dq, GP, padr);
+            *done = true;
+            return (int)cudaGetLastError();
+        }
+    }
     const int W4 = W / 4, pad = (Dq + 3) / 4 * 4 + 4;
     const int rows_cap = (kGwcThreads + W4 - 1) / W4 + 1;
     const size_t smem = (size_t)2 * CPT * rows_cap * (pad + W) * sizeof(float);
-    *done = false;
     if (smem > 100 * 1024 || (long long)G * (CPG / CPT) > 65535) return 0;
     cudaError_t e = cudaFuncSetAttribute(gwc_bwd_direct_kernel<CPG, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          100 * 1024);

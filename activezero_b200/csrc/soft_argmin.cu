@@ -105,6 +105,164 @@ __global__ void __launch_bounds__(kSAThreads) soft_argmin_fwd_kernel(const float
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Forward, packed form (what az_soft_argmin_fwd launches for the vector path).  Same algorithm as the
+// generic kernel above -- online softmax in chunks of 8 planes, exponents formed from the exact
+// difference to the running max -- with the arithmetic re-balanced for the B200 issue/XU budget
+// (round-1 ncu: XU pipe 60 %, issue 44 %, 0.89 of the read-only ceiling):
+//   * the subtract / scale / tree-sum / weighted-sum of two adjacent pixels run as ONE packed
+//     fp32x2 instruction (sub/mul/add/fma.rn.f32x2 -> FADD2/FMUL2/FFMA2): ~5 instead of ~7 issue slots
+//     per logit;
+//   * BITS: the float->double conversions of the chunk sums (XU pipe, next to the ex2) are done with
+//     integer shifts instead (an fp32 Kahan / TwoSum accumulation was emulated and rejected: the
+//     rescale products and the d0*cs term need error-free transforms to stay at the fp64 sums'
+//     2e-5 px, which costs more issue slots than it saves);
+//   * POLY > 0: the last POLY of the 8 exponentials of a chunk are evaluated on the FMA pipe
+//     (Cody-Waite split + degree-6 polynomial, packed) instead of MUFU.
+// ------------------------------------------------------------------------------------------
+typedef unsigned long long u64p;
+__device__ __forceinline__ u64p pk(float lo, float hi) { u64p r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(u64p v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64p padd(u64p a, u64p b) { u64p r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64p psub(u64p a, u64p b) { u64p r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64p pmul(u64p a, u64p b) { u64p r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64p pfma(u64p a, u64p b, u64p c) { u64p r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// 2^t for a packed pair, t <= 0, on the FMA/ALU pipes: t = n + f, n = rint(t), |f| <= 1/2,
+// 2^f = degree-6 Taylor polynomial in f*ln2 (truncation 1.2e-7 relative), scaled by 2^n through the
+// exponent field.  t is clamped at -126 (a term below 2^-126 of the maximum carries no weight).
+__device__ __forceinline__ u64p pexp2_poly(u64p t) {
+    float t0, t1;
+    upk(t, t0, t1);
+    t0 = fmaxf(t0, -126.0f);
+    t1 = fmaxf(t1, -126.0f);
+    const float kMagic = 12582912.0f;  // 1.5 * 2^23: adding it rounds to the nearest integer
+    const float r0 = __fadd_rn(t0, kMagic), r1 = __fadd_rn(t1, kMagic);
+    const u64p n = psub(pk(r0, r1), pk(kMagic, kMagic));
+    const u64p f = psub(pk(t0, t1), n);
+    // coefficients ln2^k / k!
+    u64p p = pk(1.5403530393381608e-4f, 1.5403530393381608e-4f);
+    p = pfma(p, f, pk(1.3333558146428443e-3f, 1.3333558146428443e-3f));
+    p = pfma(p, f, pk(9.6181291076284772e-3f, 9.6181291076284772e-3f));
+    p = pfma(p, f, pk(5.5504108664821580e-2f, 5.5504108664821580e-2f));
+    p = pfma(p, f, pk(2.4022650695910072e-1f, 2.4022650695910072e-1f));
+    p = pfma(p, f, pk(6.9314718055994531e-1f, 6.9314718055994531e-1f));
+    p = pfma(p, f, pk(1.0f, 1.0f));
+    float p0, p1;
+    upk(p, p0, p1);
+    // r = kMagic + n exactly, so its low mantissa bits hold n (two's complement): shift them into the exponent
+    p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+    p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+    return pk(p0, p1);
+}
+
+// float -> double for a non-negative, normal-or-zero float with integer instructions (exact for
+// normals; +0 maps to 2^-127, which no sum notices): the F2F.F64.F32 conversion runs on the XU pipe
+// next to the exponentials that bound this kernel.
+template <bool BITS>
+__device__ __forceinline__ double to_double_pos(float f) {
+    if (BITS) {
+        const unsigned u = __float_as_uint(f);
+        return __hiloint2double((int)((u >> 3) + 0x38000000u), (int)(u << 29));
+    }
+    return (double)f;
+}
+
+template <int POLY, bool BITS>
+__global__ void __launch_bounds__(kSAThreads) soft_argmin_fwd_packed_kernel(const float* __restrict__ cost,
+                                                                           float* __restrict__ disp,
+                                                                           float* __restrict__ lse, int D,
+                                                                           int64_t plane, int64_t n_vec) {
+    const int64_t t = (int64_t)blockIdx.x * kSAThreads + threadIdx.x;
+    if (t >= n_vec) return;
+    const int64_t pix = t * 4;
+    const int64_t b = pix / plane, hw = pix - b * plane;
+    const float* src = cost + b * D * plane + hw;
+    const u64p kL2 = pk(kLog2e, kLog2e);
+
+    float m[4];
+    double s[4], ws[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { m[j] = -INFINITY; s[j] = 0.0; ws[j] = 0.0; }
+
+    for (int d0 = 0; d0 < D; d0 += kChunk) {
+        float4 v[kChunk];
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k) {
+            if (d0 + k < D) v[k] = ld_stream(reinterpret_cast<const float4*>(src + (int64_t)(d0 + k) * plane));
+            else v[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+        const double dd0 = (double)d0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float xa[kChunk], xb[kChunk];
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k) {
+                xa[k] = h == 0 ? v[k].x : v[k].z;
+                xb[k] = h == 0 ? v[k].y : v[k].w;
+            }
+            float ca = xa[0], cb = xb[0];
+#pragma unroll
+            for (int k = 1; k < kChunk; ++k) { ca = fmaxf(ca, xa[k]); cb = fmaxf(cb, xb[k]); }
+            float& ma = m[2 * h];
+            float& mb = m[2 * h + 1];
+            if (ca > ma) {  // rescale the running sums (exp2(-inf) = 0 on the first chunk)
+                const double r = (double)fast_ex2((ma - ca) * kLog2e);
+                s[2 * h] *= r;
+                ws[2 * h] *= r;
+                ma = ca;
+            }
+            if (cb > mb) {
+                const double r = (double)fast_ex2((mb - cb) * kLog2e);
+                s[2 * h + 1] *= r;
+                ws[2 * h + 1] *= r;
+                mb = cb;
+            }
+            const u64p ref = pk(ma == -INFINITY ? 0.f : ma, mb == -INFINITY ? 0.f : mb);  // leading -inf planes contribute 0
+            u64p e[kChunk];
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k) {
+                const u64p a = pmul(psub(pk(xa[k], xb[k]), ref), kL2);
+                if (k >= kChunk - POLY) {
+                    e[k] = pexp2_poly(a);
+                } else {
+                    float a0, a1;
+                    upk(a, a0, a1);
+                    e[k] = pk(fast_ex2(a0), fast_ex2(a1));
+                }
+            }
+            // tree sums of the chunk in (packed) fp32, running sums in fp64
+            const u64p s01 = padd(e[0], e[1]), s23 = padd(e[2], e[3]), s45 = padd(e[4], e[5]), s67 = padd(e[6], e[7]);
+            const u64p cs = padd(padd(s01, s23), padd(s45, s67));
+            const u64p w23 = pfma(e[3], pk(3.f, 3.f), padd(e[2], e[2]));
+            const u64p w45 = pfma(e[5], pk(5.f, 5.f), pmul(e[4], pk(4.f, 4.f)));
+            const u64p w67 = pfma(e[7], pk(7.f, 7.f), pmul(e[6], pk(6.f, 6.f)));
+            const u64p cw = padd(padd(e[1], w23), padd(w45, w67));  // sum_k k*e[k], k local
+            float csa, csb, cwa, cwb;
+            upk(cs, csa, csb);
+            upk(cw, cwa, cwb);
+            const double dsa = to_double_pos<BITS>(csa), dsb = to_double_pos<BITS>(csb);
+            s[2 * h] += dsa;
+            s[2 * h + 1] += dsb;
+            ws[2 * h] += fma(dd0, dsa, to_double_pos<BITS>(cwa));
+            ws[2 * h + 1] += fma(dd0, dsb, to_double_pos<BITS>(cwb));
+        }
+    }
+    float o[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        o[j] = (float)(ws[j] / s[j]);
+        l[j] = log2f((float)s[j]);
+    }
+    *reinterpret_cast<float4*>(disp + pix) = make_float4(o[0], o[1], o[2], o[3]);
+    if (lse != nullptr) {
+        const int64_t total = n_vec * 4;
+        *reinterpret_cast<float4*>(lse + pix) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(lse + total + pix) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+
 template <int V>
 __global__ void __launch_bounds__(kSAThreads) soft_argmin_bwd_kernel(const float* __restrict__ cost,
                                                                     const float* __restrict__ disp,
@@ -161,8 +319,15 @@ extern "C" int az_soft_argmin_fwd(const float* cost, float* disp, float* lse, in
     const bool vec = (plane % 4 == 0) && aligned16(cost) && aligned16(disp) && (lse == nullptr || aligned16(lse));
     if (vec) {
         const int64_t n = total / 4;
-        soft_argmin_fwd_kernel<4><<<(unsigned)ceil_div(n, kSAThreads), kSAThreads, 0, st>>>(cost, disp, lse, (int)D,
-                                                                                           plane, n);
+        const unsigned grid = (unsigned)ceil_div(n, kSAThreads);
+        // 0 = generic kernel; 1 = packed; 2 = packed + integer conversions; 3 / 4 = (2) + 2 / 4 polynomial exp2 per chunk
+        switch (az::tuning("AZ_SA_FWD", 2)) {
+            case 0: soft_argmin_fwd_kernel<4><<<grid, kSAThreads, 0, st>>>(cost, disp, lse, (int)D, plane, n); break;
+            case 1: soft_argmin_fwd_packed_kernel<0, false><<<grid, kSAThreads, 0, st>>>(cost, disp, lse, (int)D, plane, n); break;
+            case 3: soft_argmin_fwd_packed_kernel<2, true><<<grid, kSAThreads, 0, st>>>(cost, disp, lse, (int)D, plane, n); break;
+            case 4: soft_argmin_fwd_packed_kernel<4, true><<<grid, kSAThreads, 0, st>>>(cost, disp, lse, (int)D, plane, n); break;
+            default: soft_argmin_fwd_packed_kernel<0, true><<<grid, kSAThreads, 0, st>>>(cost, disp, lse, (int)D, plane, n); break;
+        }
     } else {
         soft_argmin_fwd_kernel<1><<<(unsigned)ceil_div(total, kSAThreads), kSAThreads, 0, st>>>(cost, disp, lse, (int)D,
                                                                                                plane, total);

@@ -298,6 +298,187 @@ __global__ void __launch_bounds__(kUTW * kUTH) upsample4_soft_argmin_fwd_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Scale exactly 4 along depth AND width (D == 4*Dq, W == 4*Wq: what PSMNet runs, psmnet.py:186-211),
+// any vertical upsampling factor.  Round 1's kernel above spent 4 ex2 and ~45 issue slots per pixel and
+// depth interval (ncu: issue 80 %, XU 66 %).  This form cuts both:
+//   * a thread owns the FOUR output columns x = 4c+2 .. 4c+5 that share the low-res column pair
+//     (c, c+1): per plane it reads four taps, blends them vertically once (one packed FFMA2 + FMUL2)
+//     and expands to its four pixels with the constant weights {1/8, 3/8, 5/8, 7/8} (two FFMA2);
+//   * within a depth interval the four logits are an arithmetic progression x0 + k*diff/4, so the
+//     four exponentials are a geometric one: e_start = 2^((max(l0,l3) - m)*log2e) at the end nearer
+//     the running max and ratio r = 2^(-|diff|/4*log2e) <= 1 -- two ex2 and three multiplies;
+//   * everything per pixel pair is packed fp32x2 (FFMA2 / FADD2 / FMUL2).
+// Interval sums are collected in fp32 relative to the first depth of the current block of <= 8
+// intervals and flushed to the fp64 running sums at the end of the block or before a rescale.
+// ------------------------------------------------------------------------------------------
+typedef unsigned long long u64u;
+__device__ __forceinline__ u64u upk2f(float lo, float hi) { u64u r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void uunpk(u64u v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64u uadd(u64u a, u64u b) { u64u r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64u usub(u64u a, u64u b) { u64u r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64u umul(u64u a, u64u b) { u64u r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64u ufma(u64u a, u64u b, u64u c) { u64u r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+constexpr int kU4G = 32, kU4H = 8;  // groups (of 4 output columns) x rows per CTA
+constexpr int kU4FW = kU4G + 1;     // low-res columns under a tile (taps c and c+1)
+
+// values of the thread's four pixels on low-res plane `pl`: (v0,v1) and (v2,v3)
+__device__ __forceinline__ void bil4(const float* __restrict__ pl, int oa, int ob, u64u ly0, u64u ly1, u64u& v01,
+                                     u64u& v23) {
+    const u64u top = upk2f(pl[oa], pl[oa + 1]), bot = upk2f(pl[ob], pl[ob + 1]);
+    const u64u col = ufma(bot, ly1, umul(top, ly0));  // (colA, colB): vertical blend of the two tap columns
+    float ca, cb;
+    uunpk(col, ca, cb);
+    const float dc = cb - ca;
+    const u64u dc2 = upk2f(dc, dc), ca2 = upk2f(ca, ca);
+    v01 = ufma(upk2f(0.125f, 0.375f), dc2, ca2);
+    v23 = ufma(upk2f(0.625f, 0.875f), dc2, ca2);
+}
+
+// grid = (ceil((Wq + 1) / 32), ceil(H / 8), B), block = (32, 8).  smem: tile[Dq][fh][33]
+__global__ void __launch_bounds__(kU4G * kU4H) upsample4x_soft_argmin_fwd_kernel(
+    const float* __restrict__ low, float* __restrict__ disp, float* __restrict__ stats, int Dq, int Hq, int Wq, int H,
+    float sh, int fh_cap, int64_t total) {
+    extern __shared__ float tile[];
+    const int b = blockIdx.z, W = 4 * Wq;
+    const int c0 = blockIdx.x * kU4G - 1;  // first group of the tile (group -1 holds x = 0, 1)
+    const int y0 = blockIdx.y * kU4H, y1 = min(y0 + kU4H, H) - 1;
+    const int h_lo = src_index(sh, y0, Hq).i0, h_hi = src_index(sh, y1, Hq).i1;
+    const int fh = h_hi - h_lo + 1;
+    const int FHW = fh_cap * kU4FW;
+    {   // footprint, column / row indices clamped so that edge groups read a repeated column (=> weightless lerp)
+        const int tid = threadIdx.y * kU4G + threadIdx.x;
+        const int npos = fh * kU4FW;
+        const size_t plane = (size_t)Hq * Wq;
+        for (int pos = tid & 63; pos < npos; pos += 64) {
+            const int hh = pos / kU4FW, ww = pos - hh * kU4FW;
+            const int col = min(max(c0 + ww, 0), Wq - 1);
+            const float* srcp = low + (size_t)b * Dq * plane + (size_t)(h_lo + hh) * Wq + col;
+            for (int q = tid >> 6; q < Dq; q += (kU4G * kU4H) >> 6) tile[q * FHW + pos] = __ldg(srcp + (size_t)q * plane);
+        }
+    }
+    __syncthreads();
+    const int y = y0 + threadIdx.y;
+    const int c = c0 + threadIdx.x;
+    const int xbase = 4 * c + 2;
+    if (y >= H || xbase >= W) return;
+    const Lerp ly = src_index(sh, y, Hq);
+    const int oa = (ly.i0 - h_lo) * kU4FW + threadIdx.x, ob = (ly.i1 - h_lo) * kU4FW + threadIdx.x;
+    const u64u ly0 = upk2f(ly.l0, ly.l0), ly1 = upk2f(ly.l1, ly.l1);
+    const int D = 4 * Dq;
+    const float kQ = -0.25f * kLog2eU;
+
+    u64u va[2];
+    bil4(tile, oa, ob, ly0, ly1, va[0], va[1]);
+    float m[4];
+    uunpk(va[0], m[0], m[1]);
+    uunpk(va[1], m[2], m[3]);
+    double s[4], ws[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s[j] = 2.0; ws[j] = 1.0; }  // d = 0, 1 sample plane 0 exactly: e = 1 twice
+    u64u fs[2] = {0ull, 0ull}, fw[2] = {0ull, 0ull};           // block sums: sum e, sum (d - dblk) e
+    int qb[2] = {0, 0};                                         // first interval of the current block
+    const float* pl = tile;
+    for (int q = 0; q + 1 < Dq; ++q) {
+        pl += FHW;
+        u64u vb[2];
+        bil4(pl, oa, ob, ly0, ly1, vb[0], vb[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const u64u diff = usub(vb[h], va[h]);
+            const u64u l0 = ufma(upk2f(0.125f, 0.125f), diff, va[h]), l3 = ufma(upk2f(0.875f, 0.875f), diff, va[h]);
+            float l0a, l0b, l3a, l3b, da, db;
+            uunpk(l0, l0a, l0b);
+            uunpk(l3, l3a, l3b);
+            uunpk(diff, da, db);
+            const float cma = fmaxf(l0a, l3a), cmb = fmaxf(l0b, l3b);  // a lerp is monotone: the interval's exact max
+            float& ma = m[2 * h];
+            float& mb = m[2 * h + 1];
+            if (cma > ma || cmb > mb || q - qb[h] == 8) {
+                float fsa, fsb, fwa, fwb;
+                uunpk(fs[h], fsa, fsb);
+                uunpk(fw[h], fwa, fwb);
+                const double base = (double)(4 * qb[h] + 2);
+                s[2 * h] += (double)fsa;
+                s[2 * h + 1] += (double)fsb;
+                ws[2 * h] += fma(base, (double)fsa, (double)fwa);
+                ws[2 * h + 1] += fma(base, (double)fsb, (double)fwb);
+                fs[h] = 0ull;
+                fw[h] = 0ull;
+                qb[h] = q;
+                if (cma > ma) {
+                    const double r = (double)fast_ex2((ma - cma) * kLog2eU);
+                    s[2 * h] *= r;
+                    ws[2 * h] *= r;
+                    ma = cma;
+                }
+                if (cmb > mb) {
+                    const double r = (double)fast_ex2((mb - cmb) * kLog2eU);
+                    s[2 * h + 1] *= r;
+                    ws[2 * h + 1] *= r;
+                    mb = cmb;
+                }
+            }
+            // geometric progression from the end nearer the max
+            const u64u es = upk2f(fast_ex2((cma - ma) * kLog2eU), fast_ex2((cmb - mb) * kLog2eU));
+            const u64u r = upk2f(fast_ex2(fabsf(da) * kQ), fast_ex2(fabsf(db) * kQ));
+            const u64u f1 = umul(es, r), f2 = umul(f1, r), f3 = umul(f2, r);
+            const u64u sum = uadd(uadd(es, f1), uadd(f2, f3));
+            // sum_k k e_k: es is e_3 when diff >= 0 (3 es + 2 f1 + f2), e_0 otherwise (f1 + 2 f2 + 3 f3)
+            const u64u wup = ufma(upk2f(3.f, 3.f), es, ufma(upk2f(2.f, 2.f), f1, f2));
+            const u64u wdn = ufma(upk2f(3.f, 3.f), f3, ufma(upk2f(2.f, 2.f), f2, f1));
+            float wua, wub, wda, wdb;
+            uunpk(wup, wua, wub);
+            uunpk(wdn, wda, wdb);
+            const u64u ew = upk2f(da >= 0.f ? wua : wda, db >= 0.f ? wub : wdb);
+            const float ofs = (float)(4 * (q - qb[h]));
+            fs[h] = uadd(fs[h], sum);
+            fw[h] = uadd(fw[h], ufma(upk2f(ofs, ofs), sum, ew));
+            va[h] = vb[h];
+        }
+    }
+    float o[4], l2[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float fsa, fsb, fwa, fwb, vla, vlb;
+        uunpk(fs[h], fsa, fsb);
+        uunpk(fw[h], fwa, fwb);
+        uunpk(va[h], vla, vlb);
+        const double base = (double)(4 * qb[h] + 2);
+        const float fsv[2] = {fsa, fsb}, fwv[2] = {fwa, fwb}, vl[2] = {vla, vlb};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = 2 * h + u;
+            s[j] += (double)fsv[u];
+            ws[j] += fma(base, (double)fsv[u], (double)fwv[u]);
+            // d = D-2, D-1 sample plane Dq-1 exactly
+            if (vl[u] > m[j]) {
+                const double r = (double)fast_ex2((m[j] - vl[u]) * kLog2eU);
+                s[j] *= r;
+                ws[j] *= r;
+                m[j] = vl[u];
+            }
+            const double e = (double)fast_ex2((vl[u] - m[j]) * kLog2eU);
+            s[j] += 2.0 * e;
+            ws[j] += e * (double)(2 * D - 3);
+            o[j] = (float)(ws[j] / s[j]);
+            l2[j] = log2f((float)s[j]);
+        }
+    }
+    const size_t row = ((size_t)b * H + y) * W;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int x = xbase + 2 * h;
+        if (x < 0 || x >= W) continue;  // W = 4*Wq and x is even: a pair is wholly inside or outside
+        *reinterpret_cast<float2*>(disp + row + x) = make_float2(o[2 * h], o[2 * h + 1]);
+        if (stats != nullptr) {
+            *reinterpret_cast<float2*>(stats + row + x) = make_float2(m[2 * h], m[2 * h + 1]);
+            *reinterpret_cast<float2*>(stats + total + row + x) = make_float2(l2[2 * h], l2[2 * h + 1]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kUTW * kUTH) upsample4_soft_argmin_bwd_pix_kernel(
     const float* __restrict__ low, const float* __restrict__ disp, const float* __restrict__ stats,
     const float* __restrict__ gdisp, float* __restrict__ G, int Dq, int Hq, int Wq, int H, int W, float sh, float sw,
@@ -433,6 +614,7 @@ static int upsample_args_ok(int64_t B, int64_t Dq, int64_t Hq, int64_t Wq, int64
     if (B <= 0 || Dq <= 0 || Hq <= 0 || Wq <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
     if (D < Dq || H < Hq || W < Wq) return 0;  // upsampling only
     if (B > 65535 || H > 65535 || B * Dq > 65535 || H * W >= (1ll << 31)) return 0;
+    if (2.0 * (double)W / (double)Wq + 3.0 > kMaxTaps) return 0;  // horizontal factor <= 6: the backward's tap window
     return 1;
 }
 
@@ -447,6 +629,21 @@ extern "C" int az_upsample_soft_argmin_fwd(const float* lowres, float* disp, flo
                                          200 * 1024);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)ceil_div(W, kUTW), (unsigned)ceil_div(H, kUTH), (unsigned)B);
+    if (D == 4 * Dq && Dq >= 2 && W == 4 * Wq && az::tuning("AZ_USA_FWD", 1) == 1) {
+        // x4 in depth and width (PSMNet): 4 pixels per thread, packed arithmetic, 2 ex2 per interval
+        const int fh4 = tile_extent((int)Hq, (int)H, kU4H);
+        const size_t smem4 = (size_t)Dq * fh4 * kU4FW * sizeof(float);
+        if (smem4 <= 200 * 1024) {
+            e = cudaFuncSetAttribute(upsample4x_soft_argmin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     200 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            dim3 g4((unsigned)ceil_div(Wq + 1, kU4G), (unsigned)ceil_div(H, kU4H), (unsigned)B);
+            upsample4x_soft_argmin_fwd_kernel<<<g4, dim3(kU4G, kU4H), smem4, (cudaStream_t)stream>>>(
+                lowres, disp, stats, (int)Dq, (int)Hq, (int)Wq, (int)H, (float)Hq / (float)H, fh4, B * H * W);
+            AZ_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     if (D == 4 * Dq && Dq >= 2) {
         e = cudaFuncSetAttribute(upsample4_soft_argmin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024);
@@ -493,7 +690,6 @@ extern "C" int az_upsample_soft_argmin_bwd(const float* lowres, const float* dis
             B * H * W);
     }
     AZ_LAUNCH_CHECK();
-    if (2.0 * (double)W / (double)Wq + 3.0 > kMaxTaps) return AZ_ERR_BAD_ARG;  // horizontal upsampling factor <= 6
     dim3 gx((unsigned)ceil_div(Wq, 128), (unsigned)ceil_div(H, kRowsPerCta), (unsigned)(B * Dq));
     upsample_bwd_reduce_x_kernel<<<gx, 128, 0, st>>>(G, T, (int)H, (int)W, (int)Wq, sw);
     AZ_LAUNCH_CHECK();

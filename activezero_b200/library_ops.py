@@ -22,7 +22,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from .ops import _cuda_f32, _ptr, _stream, linspace_table
+from .ops import _cuda_f32, _mask_u8, _ptr, _stream, check_feature_pair, check_reproj_inputs, linspace_table
 
 NS = "az_stereo"
 
@@ -32,7 +32,9 @@ NS = "az_stereo"
 # ---------------------------------------------------------------------------------------------
 @torch.library.custom_op(f"{NS}::concat_volume", mutates_args=(), device_types="cuda")
 def concat_volume(ref: Tensor, tgt: Tensor, num_disp: int, channels_last: bool) -> Tensor:
-    L, R = _cuda_f32(ref, "ref"), _cuda_f32(tgt, "tgt")
+    L, R = check_feature_pair(ref, tgt, "az_stereo::concat_volume")
+    if num_disp <= 0:
+        raise ValueError("az_stereo::concat_volume: num_disp must be positive")
     B, C, H, W = L.shape
     ndhwc = channels_last and C % 4 == 0
     vol = torch.empty((B, 2 * C, num_disp, H, W), dtype=torch.float32, device=L.device,
@@ -52,6 +54,8 @@ def _(ref, tgt, num_disp, channels_last):
 
 @torch.library.custom_op(f"{NS}::concat_volume_backward", mutates_args=(), device_types="cuda")
 def concat_volume_backward(gvol: Tensor, C: int) -> Tuple[Tensor, Tensor]:
+    if gvol.dim() != 5 or gvol.shape[1] != 2 * C or not gvol.is_cuda or gvol.dtype != torch.float32:
+        raise ValueError("az_stereo::concat_volume_backward: gvol must be a CUDA float32 [B,2C,Dq,H,W] tensor")
     B, _, Dq, H, W = gvol.shape
     ndhwc = C % 4 == 0 and gvol.is_contiguous(memory_format=torch.channels_last_3d) and not gvol.is_contiguous()
     g = gvol if ndhwc else _cuda_f32(gvol, "grad_volume")
@@ -87,6 +91,8 @@ concat_volume.register_autograd(_concat_backward, setup_context=_concat_setup)
 @torch.library.custom_op(f"{NS}::soft_argmin", mutates_args=(), device_types="cuda")
 def soft_argmin_op(cost: Tensor) -> Tuple[Tensor, Tensor]:
     c = _cuda_f32(cost, "cost")
+    if c.dim() != 4:
+        raise ValueError("az_stereo::soft_argmin: cost must be [B,D,H,W]")
     B, D, H, W = c.shape
     disp = torch.empty((B, 1, H, W), dtype=torch.float32, device=c.device)
     lse = torch.empty((B, 2, H, W), dtype=torch.float32, device=c.device)
@@ -104,7 +110,14 @@ def _(cost):
 @torch.library.custom_op(f"{NS}::soft_argmin_backward", mutates_args=(), device_types="cuda")
 def soft_argmin_backward(cost: Tensor, disp: Tensor, lse: Tensor, gdisp: Tensor) -> Tensor:
     c, g = _cuda_f32(cost, "cost"), _cuda_f32(gdisp, "grad_disp")
+    if c.dim() != 4:
+        raise ValueError("az_stereo::soft_argmin_backward: cost must be [B,D,H,W]")
     B, D, H, W = c.shape
+    d_, l_ = _cuda_f32(disp, "disp"), _cuda_f32(lse, "lse")
+    if tuple(d_.shape) != (B, 1, H, W) or tuple(g.shape) != (B, 1, H, W) or tuple(l_.shape) != (B, 2, H, W) \
+            or not (d_.device == l_.device == g.device == c.device):
+        raise ValueError("az_stereo::soft_argmin_backward: disp/gdisp [B,1,H,W] and lse [B,2,H,W] on cost's device expected")
+    disp, lse = d_, l_
     gcost = torch.empty_like(c)
     with torch.cuda.device(c.device):
         _lib.call("az_soft_argmin_bwd", _ptr(c), _ptr(disp), _ptr(lse), _ptr(g), _ptr(gcost), B, D, H, W, _stream())
@@ -139,8 +152,10 @@ def soft_argmin(cost: Tensor) -> Tensor:
 @torch.library.custom_op(f"{NS}::reproj_loss", mutates_args=(), device_types="cuda")
 def reproj_loss_op(tgt: Tensor, src: Tensor, disp: Tensor, mask: Tensor, ps: int, sign: float
                    ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    t, s, d = _cuda_f32(tgt, "tgt"), _cuda_f32(src, "src"), _cuda_f32(disp, "disp")
-    m = mask.to(torch.uint8).contiguous()
+    t, s, d = check_reproj_inputs(tgt, src, disp, "az_stereo::reproj_loss")
+    m = _mask_u8(mask, t)  # [B,1,H,W] on t's device; non-zero = selected (as ops.reproj_loss)
+    if ps < 1 or ps % 2 != 1:
+        raise ValueError("az_stereo::reproj_loss: ps must be odd")
     B, C, H, W = t.shape
     dev = t.device
     warped, gpre = torch.empty_like(t), torch.empty_like(d)
@@ -162,6 +177,10 @@ def _(tgt, src, disp, mask, ps, sign):
 
 @torch.library.custom_op(f"{NS}::reproj_loss_backward", mutates_args=(), device_types="cuda")
 def reproj_loss_backward(gpre: Tensor, stats: Tensor, gloss: Tensor, sign: float, C: int, ps: int) -> Tensor:
+    if gpre.dim() != 4 or gpre.shape[1] != 1 or not gpre.is_cuda or gpre.dtype != torch.float32 \
+            or stats.numel() != 2 or stats.dtype != torch.float64 or stats.device != gpre.device:
+        raise ValueError("az_stereo::reproj_loss_backward: gpre [B,1,H,W] float32 and stats float64[2] on one CUDA device expected")
+    gpre = gpre.contiguous()
     B, _, H, W = gpre.shape
     gl = gloss.reshape(1).to(torch.float32).contiguous()
     gdisp = torch.empty_like(gpre)
@@ -193,5 +212,7 @@ reproj_loss_op.register_autograd(_rl_backward, setup_context=_rl_setup)
 def reproj_loss(tgt: Tensor, src: Tensor, disp: Tensor, mask: Tensor, ps: int = 1, sign: float = -1.0):
     """-> (loss, warped): masked MSE between ``tgt`` and ``apply_disparity(unfold(src), sign*disp)`` and the warped
     image (ps = 1) / Fold image (ps > 1); differentiable w.r.t. ``disp``."""
+    if tgt.requires_grad or src.requires_grad:
+        raise ValueError("az_stereo::reproj_loss is differentiable w.r.t. disp only; use ops.warp() for image gradients")
     loss, warped, _, _ = reproj_loss_op(tgt, src, disp, mask, ps, sign)
     return loss, warped

@@ -41,6 +41,30 @@ def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def check_feature_pair(ref_feat, tgt_feat, what: str):
+    """Shared by ops and library_ops: both features CUDA float32 [B,C,H,W] of the SAME shape and device."""
+    L = _cuda_f32(ref_feat, "ref_feat")
+    R = _cuda_f32(tgt_feat, "tgt_feat")
+    if L.dim() != 4 or L.shape != R.shape:
+        raise ValueError(f"{what}: features must both be [B,C,H,W] with identical shapes, got {tuple(L.shape)} and {tuple(R.shape)}")
+    if L.device != R.device:
+        raise ValueError(f"{what}: features live on different devices")
+    return L, R
+
+
+def check_reproj_inputs(tgt, src, disp, what: str = "reprojection loss"):
+    """tgt, src [B,C,H,W]; disp [B,1,H,W]; all CUDA float32 on one device (rejects before any C-ABI call)."""
+    t = _cuda_f32(tgt, "tgt")
+    s = _cuda_f32(src, "src")
+    d = _cuda_f32(disp, "disp")
+    if t.dim() != 4 or t.shape != s.shape or d.dim() != 4 or tuple(d.shape) != (t.shape[0], 1, t.shape[2], t.shape[3]):
+        raise ValueError(f"{what}: images [B,C,H,W] of identical shape and disp [B,1,H,W] expected, got "
+                         f"{tuple(t.shape)}, {tuple(s.shape)}, {tuple(d.shape)}")
+    if not (t.device == s.device == d.device):
+        raise ValueError(f"{what}: tensors live on different devices")
+    return t, s, d
+
+
 _LIN_CACHE: dict = {}
 
 
@@ -66,10 +90,9 @@ class ConcatVolumeFn(torch.autograd.Function):
     @staticmethod
     @_fwd32
     def forward(ctx, ref_feat, tgt_feat, num_disp: int, channels_last: bool = False):
-        L = _cuda_f32(ref_feat, "ref_feat")
-        R = _cuda_f32(tgt_feat, "tgt_feat")
-        if L.shape != R.shape or L.dim() != 4:
-            raise ValueError("concat volume: features must both be [B,C,H,W]")
+        L, R = check_feature_pair(ref_feat, tgt_feat, "concat volume")
+        if int(num_disp) <= 0:
+            raise ValueError("concat volume: num_disp must be positive")
         B, C, H, W = L.shape
         ndhwc = bool(channels_last) and C % 4 == 0
         vol = torch.empty((B, 2 * C, int(num_disp), H, W), dtype=torch.float32, device=L.device,
@@ -116,10 +139,7 @@ class GwcVolumeFn(torch.autograd.Function):
     @staticmethod
     @_fwd32
     def forward(ctx, ref_feat, tgt_feat, num_disp: int, num_groups: int):
-        L = _cuda_f32(ref_feat, "ref_feat")
-        R = _cuda_f32(tgt_feat, "tgt_feat")
-        if L.shape != R.shape or L.dim() != 4:
-            raise ValueError("gwc volume: features must both be [B,C,H,W]")
+        L, R = check_feature_pair(ref_feat, tgt_feat, "gwc volume")
         B, C, H, W = L.shape
         if C % int(num_groups) != 0:
             raise ValueError("gwc volume: C must be divisible by num_groups")
@@ -284,8 +304,8 @@ def warp(img, disp):
 def _mask_u8(mask: Optional[torch.Tensor], like: torch.Tensor) -> Optional[torch.Tensor]:
     if mask is None:
         return None
-    if not mask.is_cuda:
-        raise ValueError("mask: expected a CUDA tensor")
+    if not isinstance(mask, torch.Tensor) or not mask.is_cuda or mask.device != like.device:
+        raise ValueError("mask: expected a CUDA tensor on the images' device")
     B, _, H, W = like.shape
     if mask.dim() != 4 or mask.shape[0] != B or mask.shape[1] != 1 or mask.shape[2] != H or mask.shape[3] != W:
         raise ValueError("mask must be [B,1,H,W]")
@@ -301,11 +321,12 @@ class ReprojLossFn(torch.autograd.Function):
     @staticmethod
     @_fwd32
     def forward(ctx, tgt, src, disp, mask_u8, ps: int, sign: float, want_warped: bool):
-        t = _cuda_f32(tgt, "tgt")
-        s = _cuda_f32(src, "src")
-        d = _cuda_f32(disp, "disp")
-        if t.shape != s.shape or t.dim() != 4 or d.shape != (t.shape[0], 1, t.shape[2], t.shape[3]):
-            raise ValueError("reprojection loss: images [B,C,H,W], disp [B,1,H,W]")
+        t, s, d = check_reproj_inputs(tgt, src, disp)
+        if mask_u8 is not None and (mask_u8.dtype != torch.uint8 or tuple(mask_u8.shape) != tuple(d.shape)
+                                    or mask_u8.device != t.device or not mask_u8.is_contiguous()):
+            raise ValueError("reprojection loss: mask must be a contiguous uint8 [B,1,H,W] tensor on the images' device")
+        if int(ps) < 1 or int(ps) % 2 != 1:
+            raise ValueError("reprojection loss: ps must be odd")
         B, C, H, W = t.shape
         dev = t.device
         need_bwd = ctx.needs_input_grad[2]
@@ -351,6 +372,10 @@ def patch_fold(src, disp, ps: int, sign: float = -1.0):
     """Fold of the warped unfolded planes, cropped (reprojection.py:120-125); no grad."""
     s = _cuda_f32(src.detach(), "src")
     d = _cuda_f32(disp.detach(), "disp")
+    if s.dim() != 4 or d.dim() != 4 or tuple(d.shape) != (s.shape[0], 1, s.shape[2], s.shape[3]) or d.device != s.device:
+        raise ValueError(f"patch_fold: src [B,C,H,W] and disp [B,1,H,W] on one device expected, got {tuple(s.shape)}, {tuple(d.shape)}")
+    if int(ps) < 1 or int(ps) % 2 != 1:
+        raise ValueError("patch_fold: ps must be odd")
     B, C, H, W = s.shape
     vis = torch.empty_like(s)
     lx, ly = linspace_table(W, s.device), linspace_table(H, s.device)
@@ -358,6 +383,55 @@ def patch_fold(src, disp, ps: int, sign: float = -1.0):
         _lib.call("az_patch_fold", _ptr(s), _ptr(d), float(sign), _ptr(lx), _ptr(ly), int(ps), _ptr(vis), B, C, H, W,
                   _stream())
     return vis
+
+
+# ----------------------------------------------------------------------------
+# a9: the bilinear rescalings of the multi-scale loss (reprojection.py:153-158), one launch per scale
+# ----------------------------------------------------------------------------
+class _RescaleDispFn(torch.autograd.Function):
+    """disp_rs = F.interpolate(disp, scale_factor=r, mode="bilinear") * r together with the rescaled images and
+    mask (non-differentiable outputs); gradient w.r.t. disp through the deterministic adjoint kernel."""
+
+    @staticmethod
+    @_fwd32
+    def forward(ctx, disp, tgt, src, mask_u8, r: float):
+        t, s, d = check_reproj_inputs(tgt, src, disp, "rescale")
+        B, C, H, W = t.shape
+        Ho, Wo = int(H * r), int(W * r)  # torch: floor(in * scale_factor)
+        if Ho < 1 or Wo < 1 or r > 1.0:
+            raise ValueError("rescale: 0 < r <= 1 with a non-empty output expected")
+        inv = 1.0 / float(r)
+        dev = t.device
+        t_o = torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=dev)
+        s_o = torch.empty_like(t_o)
+        d_o = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=dev)
+        m_o = torch.empty((B, 1, Ho, Wo), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("az_bilinear_rescale_fwd", _ptr(t), _ptr(s), _ptr(d), _ptr(mask_u8), _ptr(t_o), _ptr(s_o), _ptr(d_o),
+                      _ptr(m_o), B, C, H, W, Ho, Wo, inv, inv, float(r), _stream())
+        ctx.meta = (B, H, W, Ho, Wo, inv, float(r))
+        ctx.mark_non_differentiable(t_o, s_o, m_o)
+        return d_o, t_o, s_o, m_o
+
+    @staticmethod
+    @once_differentiable
+    @_bwd
+    def backward(ctx, gd, _gt, _gs, _gm):
+        B, H, W, Ho, Wo, inv, r = ctx.meta
+        g = _cuda_f32(gd, "grad_disp_rs")
+        gin = torch.empty((B, 1, H, W), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.call("az_bilinear_rescale_bwd", _ptr(g), _ptr(gin), B, H, W, Ho, Wo, inv, inv, r, _stream())
+        return gin, None, None, None, None
+
+
+def rescale_for_loss(tgt, src, disp, mask, r: float):
+    """-> (tgt_rs, src_rs, disp_rs, mask_rs bool): the four ``F.interpolate(..., scale_factor=r, mode="bilinear")``
+    of reprojection.py:153-158 (disp additionally multiplied by r) in one kernel; differentiable w.r.t. disp."""
+    if tgt.requires_grad or src.requires_grad:
+        raise ValueError("rescale_for_loss is differentiable w.r.t. disp only")
+    d_o, t_o, s_o, m_o = _RescaleDispFn.apply(disp, tgt, src, _mask_u8(mask, tgt), float(r))
+    return t_o, s_o, d_o, m_o.view(torch.bool)
 
 
 # ----------------------------------------------------------------------------
@@ -402,6 +476,9 @@ def temporal_ir_pattern(frames, ks: int = 11, threshold: float = 0.005):
 def local_contrast_norm(image, kernel_size: int = 9, eps: float = 1e-5):
     """utils/reprojection.py:175-200 -> (normed [B,1,H,W], std [B,1,H,W])."""
     assert kernel_size % 2 == 1, "Kernel size should be odd"
+    if image.requires_grad:
+        # the reference's LCN is ordinary autograd code; this kernel is forward-only (the trainer normalises data)
+        raise ValueError("local_contrast_norm: the CUDA operator is not differentiable; detach the image first")
     im = _cuda_f32(image.detach(), "image")
     B, Cin, H, W = im.shape
     normed = torch.empty((B, 1, H, W), dtype=torch.float32, device=im.device)
@@ -425,6 +502,8 @@ def error_metric_sums(disp_gt, depth_gt, disp_pred, mask, depth_pred=None, focal
     zp = f = bl = None
     if depth_pred is not None:
         zp = _cuda_f32(depth_pred.detach(), "depth_pred")
+        if zp.shape != dg.shape or zp.device != dg.device:
+            raise ValueError("error metrics: depth_pred must be [B,1,H,W] like disp_gt, on the same device")
     else:
         f = _cuda_f32(focal_length.detach().reshape(-1), "focal_length")
         bl = _cuda_f32(baseline.detach().reshape(-1), "baseline")

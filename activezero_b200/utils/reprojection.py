@@ -62,35 +62,54 @@ def get_reprojection_error_old(input_L, input_R, pred_disp_l, mask=None):
     return loss, warped, _int_mask(mask, input_L)
 
 
+def _patch_loss_autograd(input_L, input_R, pred_disp_l, mask, ps):
+    """reprojection.py:99-127 composed from Unfold + the differentiable warp kernel: taken only when an IMAGE
+    requires grad ("feature or image" in the reference's docstring); the trainer's IR patterns never do."""
+    bs, c, h, w = input_L.shape
+    unfold = torch.nn.Unfold(kernel_size=(ps, ps), padding=(ps - 1) // 2)
+    Lu = unfold(input_L).reshape(bs, -1, h, w)
+    Ru = unfold(input_R).reshape(bs, -1, h, w)
+    Wu = ops.warp(Ru, -pred_disp_l)
+    sel = mask.repeat(1, Lu.shape[1], 1, 1) if mask is not None else torch.ones_like(Lu).type(torch.bool)
+    loss = F.mse_loss(Wu[sel], Lu[sel])
+    warped = ops.patch_fold(input_R.detach(), pred_disp_l.detach(), ps) if RETURN_WARPED_PATCH_IMAGE else None
+    return loss, warped
+
+
 def get_reproj_error_patch(input_L, input_R, pred_disp_l, mask=None, ps=5):
     """reprojection.py:99-127 -- the loss the live trainer uses (ps = 11)."""
     assert ps % 2 == 1
-    loss, warped = ops.reproj_loss(input_L, input_R, pred_disp_l, mask, ps=ps, sign=-1.0,
-                                   want_warped=RETURN_WARPED_PATCH_IMAGE)
+    if input_L.requires_grad or input_R.requires_grad:
+        loss, warped = _patch_loss_autograd(input_L, input_R, pred_disp_l, mask, ps)
+    else:
+        loss, warped = ops.reproj_loss(input_L, input_R, pred_disp_l, mask, ps=ps, sign=-1.0,
+                                       want_warped=RETURN_WARPED_PATCH_IMAGE)
     return loss, warped, _int_mask(mask, input_L)
 
 
 def get_reprojection_error_diff_ratio(input_L, input_R, pred_disp_l, mask=None):
-    """reprojection.py:130-173 (three scales; the bilinear rescaling stays torch)."""
+    """reprojection.py:130-173: three scales.  Per scale ONE kernel produces the four bilinear rescalings
+    (:153-158) and one fused kernel the warp + masked MSE; an image that requires grad takes torch's
+    F.interpolate + the differentiable warp instead."""
     ratio = [0.25, 0.5, 1]
     weight = [0.3, 0.5, 0.2]
-    if mask is not None:
-        mask = mask.repeat(1, input_L.shape[1], 1, 1)
-    else:
-        mask = torch.ones_like(input_L)
-    mask = mask.type(torch.float32).detach()
+    # reprojection.py:142-148: the C mask planes are copies of one [B,1,H,W] plane, so are their rescalings
     output, loss_dict, total_loss = {}, {}, 0
+    img_grad = input_L.requires_grad or input_R.requires_grad
+    C = input_L.shape[1]
     for i, (r, w) in enumerate(zip(ratio, weight)):
-        L_rs = F.interpolate(input_L, scale_factor=r, mode="bilinear")
-        R_rs = F.interpolate(input_R, scale_factor=r, mode="bilinear")
-        d_rs = F.interpolate(pred_disp_l, scale_factor=r, mode="bilinear") * r
-        m_rs = F.interpolate(mask, scale_factor=r, mode="bilinear").type(torch.bool)
-        # the C mask planes are copies of one [B,1,H,W] plane (:146), so are their rescalings
-        if L_rs.requires_grad or R_rs.requires_grad:
+        if img_grad:
+            mf = (mask.repeat(1, C, 1, 1) if mask is not None else torch.ones_like(input_L)).type(torch.float32).detach()
+            L_rs = F.interpolate(input_L, scale_factor=r, mode="bilinear")
+            R_rs = F.interpolate(input_R, scale_factor=r, mode="bilinear")
+            d_rs = F.interpolate(pred_disp_l, scale_factor=r, mode="bilinear") * r
+            m_rs = F.interpolate(mf, scale_factor=r, mode="bilinear").type(torch.bool)
             warped = ops.warp(R_rs, -d_rs)
             loss = F.mse_loss(warped[m_rs], L_rs[m_rs])
         else:
-            loss, warped = ops.reproj_loss(L_rs, R_rs, d_rs, m_rs[:, :1], ps=1, sign=-1.0, want_warped=True)
+            L_rs, R_rs, d_rs, m1 = ops.rescale_for_loss(input_L, input_R, pred_disp_l, mask, r)
+            loss, warped = ops.reproj_loss(L_rs, R_rs, d_rs, m1, ps=1, sign=-1.0, want_warped=True)
+            m_rs = m1.repeat(1, C, 1, 1)
         output[f"stage{i}"] = {"target": L_rs, "warped": warped, "pred_disp": d_rs, "mask": m_rs.type(torch.int)}
         loss_dict[f"stage{i}"] = loss.item()
         total_loss = total_loss + loss * w
@@ -98,5 +117,15 @@ def get_reprojection_error_diff_ratio(input_L, input_R, pred_disp_l, mask=None):
 
 
 def local_contrast_norm(image, kernel_size=9, eps=1e-5):
-    """reprojection.py:175-200 -> (normed_image, std), first channel only."""
+    """reprojection.py:175-200 -> (normed_image, std), first channel only.  Forward-only kernel (the reference
+    runs it on data inside the dataset, datasets/messytable.py:242-250); an image that requires grad takes the
+    reference's own Unfold formulation so that the call stays differentiable."""
+    if image.requires_grad:
+        ks = kernel_size
+        assert ks % 2 == 1, "Kernel size should be odd"
+        b, _, h, w = image.shape
+        img = image[:, :1]
+        patches = torch.nn.Unfold(kernel_size=(ks, ks), padding=(ks - 1) // 2)(img).reshape(b, -1, h, w)
+        mean, std = patches.mean(1, keepdim=True), patches.std(1, keepdim=True, unbiased=False)
+        return (img - mean) / (std + eps), std
     return ops.local_contrast_norm(image, kernel_size=kernel_size, eps=eps)

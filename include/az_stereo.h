@@ -125,6 +125,20 @@ int az_reproj_loss_bwd(const float* gpre, const double* stats, const float* glos
 int az_patch_fold(const float* src, const float* disp, float sign, const float* lin_x, const float* lin_y,
                   int64_t ps, float* vis, int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
 
+/* ---- a9: bilinear rescaling of the multi-scale loss -- utils/reprojection.py:153-158 ----
+ * One launch for the four F.interpolate(..., scale_factor=r, mode="bilinear") calls of one scale:
+ * tgt_o, src_o: [B,C,Ho,Wo]; disp_o = interpolate(disp) * disp_mul: [B,1,Ho,Wo] (disp may be NULL);
+ * mask_o = interpolate(mask.float()).bool(): [B,1,Ho,Wo] uint8 (mask NULL = all ones; mask_o may be NULL).
+ * scale_h, scale_w = 1/r as float32 (what torch passes to upsample_bilinear2d when scale_factor is given);
+ * Ho = floor(H*r), Wo = floor(W*r). */
+int az_bilinear_rescale_fwd(const float* tgt, const float* src, const float* disp, const uint8_t* mask,
+                            float* tgt_o, float* src_o, float* disp_o, uint8_t* mask_o,
+                            int64_t B, int64_t C, int64_t H, int64_t W, int64_t Ho, int64_t Wo,
+                            float scale_h, float scale_w, float disp_mul, void* stream);
+/* gin[B,1,H,W] = disp_mul * (adjoint of the bilinear downscaling) gout[B,1,Ho,Wo]; deterministic gather. */
+int az_bilinear_rescale_bwd(const float* gout, float* gin, int64_t B, int64_t H, int64_t W, int64_t Ho, int64_t Wo,
+                            float scale_h, float scale_w, float disp_mul, void* stream);
+
 /* ---- a10: integer scatter warp -- utils/warp_ops.py:20-47 kernels + :55-95 host ----
  * dst[n,c,y,j+disp[n,0,y,j]] = src[n,c,y,j]; among sources landing on one column the largest |disp| wins
  * (== the reference kernels' last-writer order); holes = 0.  src,dst: [N,C,H,W] float32; disp: [N,1,H,W] int32.
