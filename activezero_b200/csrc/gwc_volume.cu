@@ -425,7 +425,7 @@ static int launch_gwc_fwd(const float* L, const float* R, float* vol, int B, int
                           cudaStream_t st, bool* done) {
     const int W4 = W / 4;
     *done = false;
-    int DG = tuning("AZ_GWC_DG", 8);  // planes per CTA; 0 = round-1 kernel (all planes per CTA, rows in shared memory)
+    int DG = tuning("AZ_GWC_DG", 16);  // planes per CTA; 0 = round-1 kernel (all planes per CTA, rows in shared memory)
     if (DG > 0) {
         DG = (DG + 3) & ~3;
         const int64_t ngroups = ceil_div(Dq, DG);
@@ -454,7 +454,7 @@ static int launch_gwc_bwd(const float* gvol, const float* L, const float* R, flo
                           int H, int W, int Dq, cudaStream_t st, bool* done) {
     constexpr int CPT = CPG >= 2 ? 2 : 1;
     *done = false;
-    if (tuning("AZ_GWC_BWD", 1) == 1 && H <= 65535) {  // one-pass row kernel (TMA bulk staging)
+    if (tuning("AZ_GWC_BWD", 0) == 1 && H <= 65535) {  // one-pass row kernel (TMA bulk staging)
         const int padr = (Dq + 3) / 4 * 4 + 4, GP = (W + Dq + 8 + 3) & ~3;
         const size_t smem_row = ((size_t)(Dq + CPG) * GP + (size_t)CPG * (padr + W)) * sizeof(float);
         if (smem_row <= 200 * 1024 && (size_t)(Dq + 2 * CPG) * W * 4 < (1u << 20)) {

@@ -8,7 +8,7 @@
 //
 // torch's upsample_bilinear2d, align_corners=False, scale_factor given (so the kernel uses 1/r, not in/out):
 //   src = max((dst + 0.5) * (1/r) - 0.5, 0);  i0 = int(src);  i1 = i0 + (i0 < in-1);  l1 = src - i0;  l0 = 1 - l1
-//   out = ((h0*w0)*a + (h0*w1)*b + (h1*w0)*c) + (h1*w1)*d        (the CPU kernel's order, see blend4)
+//   out = h0*(w0*a + w1*b) + h1*(w0*c + w1*d)      (horizontal first, then vertical; see blend4)
 #include "common.cuh"
 
 namespace az {
@@ -29,16 +29,14 @@ __device__ __forceinline__ Lin1 lin_index(float scale, int dst, int in_size) {
     return r;
 }
 
-// torch's CPU kernel (what the oracle and the reference's CPU path run) forms the four corner weights first and
-// accumulates ((w00*a + w01*b) + w10*c) + w11*d; for the ratios the loss uses (1/4, 1/2, 1) every product is exact
-// and this order reproduces F.interpolate bit for bit (checked against torch 2.11 CPU in the authoring container).
+// torch's CUDA kernel (upsample_bilinear2d_out_frame: what the reference runs) and its CPU kernel at realistic
+// image sizes both evaluate h0*(w0*a + w1*b) + h1*(w0*c + w1*d): horizontal first, then vertical.  (For small
+// outputs the CPU kernel switches to four pre-multiplied corner weights, which differs in the last bit; checked in
+// the authoring container with torch 2.11.)  The same order, un-fused, reproduces F.interpolate bit for bit.
 __device__ __forceinline__ float blend4(float a, float b, float c, float d, const Lin1& ly, const Lin1& lx) {
-    const float w00 = __fmul_rn(ly.l0, lx.l0), w01 = __fmul_rn(ly.l0, lx.l1);
-    const float w10 = __fmul_rn(ly.l1, lx.l0), w11 = __fmul_rn(ly.l1, lx.l1);
-    float acc = __fmul_rn(w00, a);
-    acc = __fadd_rn(acc, __fmul_rn(w01, b));
-    acc = __fadd_rn(acc, __fmul_rn(w10, c));
-    return __fadd_rn(acc, __fmul_rn(w11, d));
+    const float top = __fadd_rn(__fmul_rn(lx.l0, a), __fmul_rn(lx.l1, b));
+    const float bot = __fadd_rn(__fmul_rn(lx.l0, c), __fmul_rn(lx.l1, d));
+    return __fadd_rn(__fmul_rn(ly.l0, top), __fmul_rn(ly.l1, bot));
 }
 
 __device__ __forceinline__ float bil_sample(const float* __restrict__ p, int W, const Lin1& ly, const Lin1& lx) {

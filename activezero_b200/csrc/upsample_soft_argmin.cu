@@ -309,8 +309,11 @@ __global__ void __launch_bounds__(kUTW * kUTH) upsample4_soft_argmin_fwd_kernel(
 //     four exponentials are a geometric one: e_start = 2^((max(l0,l3) - m)*log2e) at the end nearer
 //     the running max and ratio r = 2^(-|diff|/4*log2e) <= 1 -- two ex2 and three multiplies;
 //   * everything per pixel pair is packed fp32x2 (FFMA2 / FADD2 / FMUL2).
-// Interval sums are collected in fp32 relative to the first depth of the current block of <= 8
-// intervals and flushed to the fp64 running sums at the end of the block or before a rescale.
+//   * two passes over the shared-memory tile: first the exact per-pixel maximum (max over the Dq
+//     interpolated planes), then the sums against that fixed reference -- no rescale and no data-dependent
+//     branch in the hot loop;
+// Interval sums are collected in fp32 relative to the first depth of the current block of 8 intervals and
+// flushed to the fp64 running sums at the end of the block.
 // ------------------------------------------------------------------------------------------
 typedef unsigned long long u64u;
 __device__ __forceinline__ u64u upk2f(float lo, float hi) { u64u r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
@@ -369,59 +372,79 @@ __global__ void __launch_bounds__(kU4G * kU4H) upsample4x_soft_argmin_fwd_kernel
     const int D = 4 * Dq;
     const float kQ = -0.25f * kLog2eU;
 
+    // pass 1: the exact maximum of every pixel's D logits.  The samples of interval q lie at 1/8 .. 7/8 between
+    // planes q and q+1 (a lerp is monotone: the interval's maximum is its first or last sample), d = 0, 1 sample
+    // plane 0 and d = D-2, D-1 plane Dq-1 exactly.  (The maximum over the PLANES would not do: with logits in the
+    // thousands every sample can sit hundreds below the nearest plane and all exponentials would underflow.)
+    // With the reference fixed up front, pass 2 has no rescale, no data-dependent branch (round 1's one-pass form
+    // took its fp64 flush-and-rescale branch on almost every interval of almost every warp) and no per-interval
+    // float->double conversion.
+    float m[4];
+    {
+        u64u pa[2], pb[2];
+        bil4(tile, oa, ob, ly0, ly1, pa[0], pa[1]);
+        uunpk(pa[0], m[0], m[1]);
+        uunpk(pa[1], m[2], m[3]);
+        const float* pq = tile;
+        for (int q = 1; q < Dq; ++q) {
+            pq += FHW;
+            bil4(pq, oa, ob, ly0, ly1, pb[0], pb[1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const u64u diff = usub(pb[h], pa[h]);
+                float a0, a1, b0, b1;
+                uunpk(ufma(upk2f(0.125f, 0.125f), diff, pa[h]), a0, a1);
+                uunpk(ufma(upk2f(0.875f, 0.875f), diff, pa[h]), b0, b1);
+                m[2 * h] = fmaxf(m[2 * h], fmaxf(a0, b0));
+                m[2 * h + 1] = fmaxf(m[2 * h + 1], fmaxf(a1, b1));
+                pa[h] = pb[h];
+            }
+        }
+        float l0, l1, l2, l3;
+        uunpk(pa[0], l0, l1);
+        uunpk(pa[1], l2, l3);
+        m[0] = fmaxf(m[0], l0);
+        m[1] = fmaxf(m[1], l1);
+        m[2] = fmaxf(m[2], l2);
+        m[3] = fmaxf(m[3], l3);
+    }
+    const u64u m2[2] = {upk2f(m[0], m[1]), upk2f(m[2], m[3])};
+    const u64u kL2 = upk2f(kLog2eU, kLog2eU);
+
+    // pass 2
     u64u va[2];
     bil4(tile, oa, ob, ly0, ly1, va[0], va[1]);
-    float m[4];
-    uunpk(va[0], m[0], m[1]);
-    uunpk(va[1], m[2], m[3]);
     double s[4], ws[4];
+    {   // d = 0, 1 sample plane 0 exactly
+        float e[4], t0, t1;
+        uunpk(umul(usub(va[0], m2[0]), kL2), t0, t1);
+        e[0] = fast_ex2(t0);
+        e[1] = fast_ex2(t1);
+        uunpk(umul(usub(va[1], m2[1]), kL2), t0, t1);
+        e[2] = fast_ex2(t0);
+        e[3] = fast_ex2(t1);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { s[j] = 2.0; ws[j] = 1.0; }  // d = 0, 1 sample plane 0 exactly: e = 1 twice
-    u64u fs[2] = {0ull, 0ull}, fw[2] = {0ull, 0ull};           // block sums: sum e, sum (d - dblk) e
-    int qb[2] = {0, 0};                                         // first interval of the current block
+        for (int j = 0; j < 4; ++j) { s[j] = 2.0 * (double)e[j]; ws[j] = (double)e[j]; }
+    }
+    u64u fs[2] = {0ull, 0ull}, fw[2] = {0ull, 0ull};  // block sums: sum e, sum (d - dblk) e over <= 8 intervals
+    int qb = 0;                                      // first interval of the current block
     const float* pl = tile;
     for (int q = 0; q + 1 < Dq; ++q) {
         pl += FHW;
         u64u vb[2];
         bil4(pl, oa, ob, ly0, ly1, vb[0], vb[1]);
+        const float ofs = (float)(4 * (q - qb));
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const u64u diff = usub(vb[h], va[h]);
             const u64u l0 = ufma(upk2f(0.125f, 0.125f), diff, va[h]), l3 = ufma(upk2f(0.875f, 0.875f), diff, va[h]);
-            float l0a, l0b, l3a, l3b, da, db;
+            float l0a, l0b, l3a, l3b, da, db, ta, tb;
             uunpk(l0, l0a, l0b);
             uunpk(l3, l3a, l3b);
             uunpk(diff, da, db);
-            const float cma = fmaxf(l0a, l3a), cmb = fmaxf(l0b, l3b);  // a lerp is monotone: the interval's exact max
-            float& ma = m[2 * h];
-            float& mb = m[2 * h + 1];
-            if (cma > ma || cmb > mb || q - qb[h] == 8) {
-                float fsa, fsb, fwa, fwb;
-                uunpk(fs[h], fsa, fsb);
-                uunpk(fw[h], fwa, fwb);
-                const double base = (double)(4 * qb[h] + 2);
-                s[2 * h] += (double)fsa;
-                s[2 * h + 1] += (double)fsb;
-                ws[2 * h] += fma(base, (double)fsa, (double)fwa);
-                ws[2 * h + 1] += fma(base, (double)fsb, (double)fwb);
-                fs[h] = 0ull;
-                fw[h] = 0ull;
-                qb[h] = q;
-                if (cma > ma) {
-                    const double r = (double)fast_ex2((ma - cma) * kLog2eU);
-                    s[2 * h] *= r;
-                    ws[2 * h] *= r;
-                    ma = cma;
-                }
-                if (cmb > mb) {
-                    const double r = (double)fast_ex2((mb - cmb) * kLog2eU);
-                    s[2 * h + 1] *= r;
-                    ws[2 * h + 1] *= r;
-                    mb = cmb;
-                }
-            }
-            // geometric progression from the end nearer the max
-            const u64u es = upk2f(fast_ex2((cma - ma) * kLog2eU), fast_ex2((cmb - mb) * kLog2eU));
+            // geometric progression from the end nearer the max: e_start, then ratio r = 2^(-|diff|/4 log2e) <= 1
+            uunpk(umul(usub(upk2f(fmaxf(l0a, l3a), fmaxf(l0b, l3b)), m2[h]), kL2), ta, tb);
+            const u64u es = upk2f(fast_ex2(ta), fast_ex2(tb));
             const u64u r = upk2f(fast_ex2(fabsf(da) * kQ), fast_ex2(fabsf(db) * kQ));
             const u64u f1 = umul(es, r), f2 = umul(f1, r), f3 = umul(f2, r);
             const u64u sum = uadd(uadd(es, f1), uadd(f2, f3));
@@ -432,34 +455,39 @@ __global__ void __launch_bounds__(kU4G * kU4H) upsample4x_soft_argmin_fwd_kernel
             uunpk(wup, wua, wub);
             uunpk(wdn, wda, wdb);
             const u64u ew = upk2f(da >= 0.f ? wua : wda, db >= 0.f ? wub : wdb);
-            const float ofs = (float)(4 * (q - qb[h]));
             fs[h] = uadd(fs[h], sum);
             fw[h] = uadd(fw[h], ufma(upk2f(ofs, ofs), sum, ew));
             va[h] = vb[h];
         }
+        if (q - qb == 7 || q + 2 == Dq) {  // uniform: flush the block into the fp64 running sums
+            const double base = (double)(4 * qb + 2);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float fsa, fsb, fwa, fwb;
+                uunpk(fs[h], fsa, fsb);
+                uunpk(fw[h], fwa, fwb);
+                s[2 * h] += (double)fsa;
+                s[2 * h + 1] += (double)fsb;
+                ws[2 * h] += fma(base, (double)fsa, (double)fwa);
+                ws[2 * h + 1] += fma(base, (double)fsb, (double)fwb);
+                fs[h] = 0ull;
+                fw[h] = 0ull;
+            }
+            qb = q + 1;
+        }
     }
     float o[4], l2[4];
+    {   // d = D-2, D-1 sample plane Dq-1 exactly
+        float vl[4], t0, t1;
+        uunpk(umul(usub(va[0], m2[0]), kL2), t0, t1);
+        vl[0] = fast_ex2(t0);
+        vl[1] = fast_ex2(t1);
+        uunpk(umul(usub(va[1], m2[1]), kL2), t0, t1);
+        vl[2] = fast_ex2(t0);
+        vl[3] = fast_ex2(t1);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        float fsa, fsb, fwa, fwb, vla, vlb;
-        uunpk(fs[h], fsa, fsb);
-        uunpk(fw[h], fwa, fwb);
-        uunpk(va[h], vla, vlb);
-        const double base = (double)(4 * qb[h] + 2);
-        const float fsv[2] = {fsa, fsb}, fwv[2] = {fwa, fwb}, vl[2] = {vla, vlb};
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int j = 2 * h + u;
-            s[j] += (double)fsv[u];
-            ws[j] += fma(base, (double)fsv[u], (double)fwv[u]);
-            // d = D-2, D-1 sample plane Dq-1 exactly
-            if (vl[u] > m[j]) {
-                const double r = (double)fast_ex2((m[j] - vl[u]) * kLog2eU);
-                s[j] *= r;
-                ws[j] *= r;
-                m[j] = vl[u];
-            }
-            const double e = (double)fast_ex2((vl[u] - m[j]) * kLog2eU);
+        for (int j = 0; j < 4; ++j) {
+            const double e = (double)vl[j];
             s[j] += 2.0 * e;
             ws[j] += e * (double)(2 * D - 3);
             o[j] = (float)(ws[j] / s[j]);

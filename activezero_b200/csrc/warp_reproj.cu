@@ -525,6 +525,10 @@ namespace az {
 int plf_dispatch(const float* tgt, const float* src, const float* disp, float sign, const uint8_t* mask,
                  const float* lin_x, const float* lin_y, int ps, float* vis, float* gpre, double* partial, int B, int C,
                  int H, int W, int* nbands_out, cudaStream_t st);
+// patch_loss_fold_v3.cu: round-2 form of the same pass (lanes over tap rows: conflict-free window loads)
+int plf3_dispatch(const float* tgt, const float* src, const float* disp, float sign, const uint8_t* mask,
+                  const float* lin_x, const float* lin_y, int ps, float* vis, float* gpre, double* partial, int B, int C,
+                  int H, int W, int* nbands_out, cudaStream_t st);
 }
 
 extern "C" int az_warp_fwd(const float* img, const float* disp, const float* lin_x, const float* lin_y, float* out,
@@ -591,9 +595,13 @@ extern "C" int az_reproj_loss_fwd(const float* tgt, const float* src, const floa
         cudaError_t e = cudaMemsetAsync(warped, 0, (size_t)B * C * H * W * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
         int nbands = 0;
-        rc = H > (1 << 24) ? AZ_ERR_BAD_ARG
-                           : plf_dispatch(tgt, src, disp, sign, mask, lin_x, lin_y, (int)ps, warped, gpre, partial, (int)B,
-                                          (int)C, (int)H, (int)W, &nbands, st);
+        rc = AZ_ERR_BAD_ARG;
+        if (H <= (1 << 24) && tuning("AZ_PATCH_IMPL", 1) == 1)
+            rc = plf3_dispatch(tgt, src, disp, sign, mask, lin_x, lin_y, (int)ps, warped, gpre, partial, (int)B, (int)C,
+                               (int)H, (int)W, &nbands, st);
+        if (rc == AZ_ERR_BAD_ARG && H <= (1 << 24))
+            rc = plf_dispatch(tgt, src, disp, sign, mask, lin_x, lin_y, (int)ps, warped, gpre, partial, (int)B, (int)C,
+                              (int)H, (int)W, &nbands, st);
         if (rc == 0) {
             reproj_finalize_kernel<<<1, 1024, 0, st>>>(partial, B * nbands, (double)(C * ps * ps), loss_out, stats);
             AZ_LAUNCH_CHECK();

@@ -44,6 +44,11 @@ WORKLOAD = (f"config2: PSMNet inference hot path fwd, batch {B} x {H}x{W}, D={D}
             f"[{B},{2 * C},{DQ},{HQ},{WQ}] + soft-argmin [{B},{D},{H},{W}] + patch reprojection loss ps={PS} (+fold image); "
             f"logits = trilinear upsample of random [{DQ},{HQ},{WQ}] logits as psmnet.py:186-197 produces them")
 
+# identical in both arms (the driver compares the dicts): what one step processes and how it is sharded
+CONFIG = {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "sharding": "batch (pairs) per rank, no data-path collective",
+          "l2": "inputs larger than L2: 6.5 GB streamed per step vs 126 MB L2"}
+NOMINAL_HBM_GBS = 8000.0  # the ~8 TB/s the north star quotes (DGX figure; HGX B200: 7.7 TB/s)
+
 # algorithmic bytes per launch (SURVEY.md §8d formulas x B pairs), fp32
 ALGO_BYTES = {
     "concat_volume_fwd": 4 * (2 * C * HQ * WQ + 2 * C * DQ * HQ * WQ) * B,
@@ -54,9 +59,16 @@ ALGO_BYTES = {
 
 # training hot path per pair: concat fwd+bwd, 3 x soft-argmin fwd+bwd, patch reprojection fwd+bwd
 TRAIN_B, TRAIN_STEPS = 2, 10
+TRAIN_BATCHES = (2, 8)   # the reference's per-GPU batch (configs/config.py:93) and the bench batch
+STOCK_B = 2
 TRAIN_BYTES_PER_PAIR = (2 * 4 * (2 * C * HQ * WQ + 2 * C * DQ * HQ * WQ) + 3 * (4 * (D * H * W + H * W) + 4 * (2 * D * H * W + 2 * H * W))
                         + 4 * 3 * H * W + H * W + 4 * H * W)
-BOUND = {"concat_volume_fwd": "hbm", "soft_argmin_fwd": "hbm", "reproj_patch_loss+fold_fwd": "shared-memory bandwidth (LSU wavefronts)"}
+BOUND = {"concat_volume_fwd": "hbm", "soft_argmin_fwd": "hbm", "reproj_patch_loss+fold_fwd": "lsu (shared-memory wavefronts)"}
+NUM_SMS = 148
+FUSED_EX2 = (2 * (DQ - 1) + 4) * H * W * B   # ex2 per launch of the fused upsample + soft-argmin kernel
+_VOL, _FEAT, _LOG, _IMG = 4 * 2 * C * DQ * HQ * WQ, 4 * 2 * C * HQ * WQ, 4 * D * H * W, 4 * H * W
+TRAIN_PHASE_BYTES = {"concat_fwd": _VOL + _FEAT, "concat_bwd": _VOL + _FEAT, "soft_argmin_fwd_x3": 3 * (_LOG + 3 * _IMG),
+                     "soft_argmin_bwd_x3": 3 * (2 * _LOG + 4 * _IMG)}  # per pair
 
 
 def _peaks():
@@ -147,6 +159,58 @@ def cpu_reference_step(inputs, so):
     return vol, disp, loss, vis
 
 
+def stock_torch_step(L, R, cost, pat_L, pat_R, mask):
+    """The reference's dataflow with stock torch operators on whatever device the inputs live on
+    (psmnet.py:151-165, :200-201 + psmnet_submodule.py:80-89, utils/reprojection.py:13-35 and :99-127)."""
+    import torch.nn.functional as F
+
+    nb, c, hq, wq = L.shape
+    vol = torch.zeros(nb, 2 * c, DQ, hq, wq, device=L.device)
+    for i in range(DQ):
+        if i > 0:
+            vol[:, :c, i, :, i:] = L[:, :, :, i:]
+            vol[:, c:, i, :, i:] = R[:, :, :, :-i]
+        else:
+            vol[:, :c, i] = L
+            vol[:, c:, i] = R
+    prob = F.softmax(cost, dim=1)
+    disp = torch.sum(prob * torch.arange(D, device=cost.device, dtype=torch.float32).view(1, D, 1, 1), 1, keepdim=True)
+    bs, ch, h, w = pat_L.shape
+    unfold = torch.nn.Unfold(kernel_size=(PS, PS), padding=(PS - 1) // 2)
+    Lu = unfold(pat_L).reshape(bs, -1, h, w)
+    Ru = unfold(pat_R).reshape(bs, -1, h, w)
+    xb = torch.linspace(0, 1, w, device=L.device).repeat(bs, h, 1)
+    yb = torch.linspace(0, 1, h, device=L.device).repeat(bs, w, 1).transpose(1, 2)
+    flow = torch.stack((xb + (-disp[:, 0]) / w, yb), dim=3)
+    Wu = F.grid_sample(Ru, 2 * flow - 1, mode="bilinear", padding_mode="zeros", align_corners=False)
+    sel = mask.repeat(1, Lu.shape[1], 1, 1)
+    loss = F.mse_loss(Wu[sel], Lu[sel])
+    fold = torch.nn.Fold(output_size=(h, w), kernel_size=(PS, PS), padding=(PS - 1) // 2)
+    vis = fold(Wu.reshape(bs, -1, h * w))
+    return vol, disp, loss, vis
+
+
+def time_stock_torch_gpu(L, R, cost, pat_L, pat_R, mask, steps=5):
+    with torch.no_grad():
+        for _ in range(2):
+            stock_torch_step(L, R, cost, pat_L, pat_R, mask)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(steps):
+            out = stock_torch_step(L, R, cost, pat_L, pat_R, mask)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        loss = float(out[2])
+        del out
+    torch.cuda.empty_cache()
+    nb = L.shape[0]
+    return {"note": "informational: the same forward step with STOCK torch operators on this B200 (the reference's own "
+                    "dataflow; the reference hard-codes .cuda(), so this is its execution target)",
+            "pairs_per_step": nb, "ms_per_step": ms, "value": nb / (ms * 1e-3), "unit": UNIT, "loss_check": loss}
+
+
 def make_inputs(nb, seed, device="cpu", pin=False):
     g = torch.Generator().manual_seed(seed)
     L = torch.randn(nb, C, HQ, WQ, generator=g)
@@ -195,7 +259,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": pairs_s, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": CONFIG, "sample": sample,
+        "note": "the reference runs this path on CUDA (hard-coded .cuda()); this arm is its torch code on the host cores, "
+                "as the tier contract asks -- the same-GPU comparison is the B200 arm's variant_stock_torch_gpu",
         "cpu_baseline": {"value": pairs_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": pairs_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -273,11 +339,40 @@ def run_b200(args, rank, world, local_rank):
         h2d = sum(t.numel() * t.element_size() for t in host)
         d2h = res_disp.numel() * 4 + 4
 
+        # The step is pipelined over two streams: the 3.2 GB of logits are shipped pair by pair on a copy stream
+        # (one cudaMemcpyAsync per tensor per pair) while the compute stream runs the soft-argmin of the pairs that
+        # have landed; the small inputs go first, the batch-level calls (volume, patch loss over the whole batch,
+        # as the reference computes its masked mean) follow the last pair, and the results return on the copy stream.
+        copy_stream = torch.cuda.Stream(device=dev)
+        dev_in = [torch.empty_like(t, device=dev) for t in host]
+        disp_buf = torch.empty((n_pairs, 1, H, W), dtype=torch.float32, device=dev)
+        pair_ready = [torch.cuda.Event() for _ in range(n_pairs)]
+        small_ready, done_ev, reuse_ev = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+
         def e2e_step():
-            dv = [t.to(dev, non_blocking=True) for t in host]
-            _, disp, loss, _ = az_call(dv)
-            res_disp.copy_(disp, non_blocking=True)
-            res_loss.copy_(loss, non_blocking=True)
+            comp = torch.cuda.current_stream()
+            copy_stream.wait_event(reuse_ev)  # the previous step no longer reads the staging buffers
+            with torch.cuda.stream(copy_stream):
+                for k in (0, 1, 3, 4, 5):
+                    dev_in[k].copy_(host[k], non_blocking=True)
+                small_ready.record(copy_stream)
+                for j in range(n_pairs):
+                    dev_in[2][j].copy_(host[2][j], non_blocking=True)
+                    pair_ready[j].record(copy_stream)
+            comp.wait_event(small_ready)
+            vol = ops.build_concat_volume(dev_in[0], dev_in[1], DQ)
+            for j in range(n_pairs):
+                comp.wait_event(pair_ready[j])
+                disp_buf[j:j + 1] = ops.soft_argmin(dev_in[2][j:j + 1])
+            loss, vis, _ = az_rp.get_reproj_error_patch(dev_in[3], dev_in[4], disp_buf, dev_in[5], ps=PS)
+            done_ev.record(comp)
+            reuse_ev.record(comp)
+            copy_stream.wait_event(done_ev)
+            with torch.cuda.stream(copy_stream):
+                res_disp.copy_(disp_buf, non_blocking=True)
+                res_loss.copy_(loss, non_blocking=True)
+            comp.wait_stream(copy_stream)
+            return vol, vis
 
         def az_call(dv):
             # the call a user makes: the reference-named functions of the drop-in modules
@@ -286,6 +381,7 @@ def run_b200(args, rank, world, local_rank):
             loss, vis, _ = az_rp.get_reproj_error_patch(dv[3], dv[4], disp, dv[5], ps=PS)
             return vol, disp, loss, vis
 
+        reuse_ev.record(torch.cuda.current_stream())
         for _ in range(2):
             e2e_step()
         s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -299,6 +395,16 @@ def run_b200(args, rank, world, local_rank):
         clocks.pause()
         ms_e2e = s2.elapsed_time(e2)
         loss_val = float(res_loss)
+        # the host link alone: the same pinned buffers, H2D only, all ranks at once (barrier on both sides)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        h0.record()
+        for _ in range(3):
+            for k in range(len(host)):
+                dev_in[k].copy_(host[k], non_blocking=True)
+        h1.record()
+        barrier()
+        ms_h2d = h0.elapsed_time(h1) / 3
 
         # ---- informational variant: the same step when the soft-argmin is fed by the
         # LOW-RESOLUTION logits and fused with the trilinear upsample, i.e. the [B,192,544,960] tensor is
@@ -306,9 +412,15 @@ def run_b200(args, rank, world, local_rank):
         low_host = (torch.randn(n_pairs, 1, DQ, HQ, WQ, generator=torch.Generator().manual_seed(7 + first_pair)) * 4.0).pin_memory()
         low_dev = low_host.to(dev)
 
-        def fused_step(Ld, Rd, lowd, pLd, pRd, md):
+        fk = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+
+        def fused_step(Ld, Rd, lowd, pLd, pRd, md, ev=None):
             vol = ops.build_concat_volume(Ld, Rd, DQ)
+            if ev is not None:
+                ev[0].record()
             disp = ops.upsample_soft_argmin(lowd, (D, H, W))
+            if ev is not None:
+                ev[1].record()
             loss, vis = ops.reproj_loss(pLd, pRd, disp, md, ps=PS, sign=-1.0, want_warped=True)
             return vol, disp, loss, vis
 
@@ -325,52 +437,82 @@ def run_b200(args, rank, world, local_rank):
         f0, f1, f2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         barrier()
         f0.record()
-        for _ in range(args.steps):
-            fused_step(L, R, low_dev, pat_L, pat_R, mask)
+        for k in range(args.steps):
+            fused_step(L, R, low_dev, pat_L, pat_R, mask, fk[k])
         f1.record()
         for _ in range(e2e_steps):
             fused_e2e_step()
         f2.record()
         barrier()
         ms_fused, ms_fused_e2e = f0.elapsed_time(f1), f1.elapsed_time(f2)
+        ms_fused_k = statistics.fmean(a_.elapsed_time(b_) for a_, b_ in fk)
         h2d_fused = h2d - host[2].numel() * 4 + low_host.numel() * 4
 
         # ---- informational variant: the TRAINING hot path (BASELINE target "fwd/bwd"), forward and backward of
         # concat volume + three soft-argmin heads (psmnet.py:200-217) + patch reprojection loss on the last head,
-        # at the same frame size, TRAIN_B pairs per step, device-resident.  The upstream gradients of the volume
-        # and of the three heads are synthetic tensors (in the network they come from dres0 and the smooth-L1 loss).
+        # at the same frame size, device-resident, at the reference's per-GPU batch (2) and at the bench batch (8).
+        # The upstream gradients of the volume and of the three heads are synthetic tensors (in the network they
+        # come from dres0 and the smooth-L1 loss).  Each phase is bracketed by CUDA events.
         del low_dev
         ms_train = float("nan")
+        train_rows = {}
         if not args.no_train_variant:
-            tb = TRAIN_B
-            with torch.enable_grad():
-                Lt, Rt = L[:tb].clone().requires_grad_(True), R[:tb].clone().requires_grad_(True)
-                heads = [cost[:tb].clone().requires_grad_(True) for _ in range(3)]
-                gvol = torch.randn(tb, 2 * C, DQ, HQ, WQ, device=dev)
-                gheads = [torch.randn(tb, 1, H, W, device=dev) for _ in range(3)]
+            phases = ["concat_fwd", "soft_argmin_fwd_x3", "reproj_patch_fwd", "reproj_patch_bwd", "soft_argmin_bwd_x3", "concat_bwd"]
+            for tb in TRAIN_BATCHES:
+                with torch.enable_grad():
+                    Lt, Rt = L[:tb].clone().requires_grad_(True), R[:tb].clone().requires_grad_(True)
+                    heads = [cost[:tb].clone().requires_grad_(True) for _ in range(3)]
+                    gvol = torch.randn(tb, 2 * C, DQ, HQ, WQ, device=dev)
+                    gheads = [torch.randn(tb, 1, H, W, device=dev) for _ in range(3)]
+                    tev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(phases) + 1)] for _ in range(TRAIN_STEPS)]
 
-                def train_step():
-                    for t in [Lt, Rt] + heads:
-                        t.grad = None
-                    vol = ops.build_concat_volume(Lt, Rt, DQ)
-                    d1, d2, d3 = (ops.soft_argmin(c_) for c_ in heads)
-                    loss, _, _ = az_rp.get_reproj_error_patch(pat_L[:tb], pat_R[:tb], d3, mask[:tb], ps=PS)
-                    torch.autograd.backward([vol, d1, d2, d3, loss], [gvol] + gheads + [None])
+                    def train_step(ev=None):
+                        def mark(i_):
+                            if ev is not None:
+                                ev[i_].record()
+                        for t in [Lt, Rt] + heads:
+                            t.grad = None
+                        mark(0)
+                        vol = ops.build_concat_volume(Lt, Rt, DQ)
+                        mark(1)
+                        d1, d2, d3 = (ops.soft_argmin(c_) for c_ in heads)
+                        mark(2)
+                        loss, _, _ = az_rp.get_reproj_error_patch(pat_L[:tb], pat_R[:tb], d3, mask[:tb], ps=PS)
+                        mark(3)
+                        gd3, = torch.autograd.grad(loss, d3)
+                        mark(4)
+                        torch.autograd.backward([d1, d2, d3], [gheads[0], gheads[1], gheads[2] + gd3])
+                        mark(5)
+                        vol.backward(gvol)
+                        mark(6)
 
-                for _ in range(3):
-                    train_step()
-                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                barrier()
-                t0.record()
-                for _ in range(TRAIN_STEPS):
-                    train_step()
-                t1.record()
-                barrier()
-                ms_train = t0.elapsed_time(t1)
-                del Lt, Rt, heads, gvol, gheads
+                    for _ in range(3):
+                        train_step()
+                    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    barrier()
+                    t0.record()
+                    for k in range(TRAIN_STEPS):
+                        train_step(tev[k])
+                    t1.record()
+                    barrier()
+                    ms_tb = t0.elapsed_time(t1)
+                    train_rows[tb] = {"ms_total": ms_tb, "phases": {
+                        n_: statistics.fmean(tev[k][i_].elapsed_time(tev[k][i_ + 1]) for k in range(TRAIN_STEPS))
+                        for i_, n_ in enumerate(phases)}}
+                    if tb == TRAIN_B:
+                        ms_train = ms_tb
+                    del Lt, Rt, heads, gvol, gheads
 
-    ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train = dist_util.max_over_ranks(
-        [ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train], dev)
+        # ---- informational: the SAME forward step with stock torch operators on this GPU (the reference's own
+        # dataflow: zero volume + 96 slice copies, softmax + regression, Unfold + grid_sample + boolean gathers + Fold),
+        # STOCK_B pairs.  This, not the CPU arm, is the like-for-like baseline: the reference runs on CUDA.
+        stock = None
+        if world == 1 and not args.no_stock_variant:
+            stock = time_stock_torch_gpu(L[:STOCK_B], R[:STOCK_B], cost[:STOCK_B], pat_L[:STOCK_B], pat_R[:STOCK_B],
+                                         mask[:STOCK_B])
+
+    ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train, ms_h2d, ms_fused_k = dist_util.max_over_ranks(
+        [ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train, ms_h2d, ms_fused_k], dev)
 
     if rank == 0:
         per_kernel = {}
@@ -378,12 +520,29 @@ def run_b200(args, rank, world, local_rank):
             per_kernel[n] = statistics.fmean(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps))
         peak, peak_src = _peaks()
         traffic = _traffic()
+        clk = clocks.result()
+        sm_hz = (clk.get("sm_mhz") or 1965) * 1e6
         kernels = []
         for n in names:
             gbs = ALGO_BYTES[n] / (per_kernel[n] * 1e-3) / 1e9
-            kernels.append({"kernel": n, "ms": per_kernel[n], "algo_bytes": ALGO_BYTES[n], "achieved_gbs": gbs,
-                            "frac": gbs / peak, "share": per_kernel[n] / sum(per_kernel.values()),
-                            "traffic": traffic.get(n), "bound": BOUND[n]})
+            tr = traffic.get(n)
+            row = {"kernel": n, "ms": per_kernel[n], "share": per_kernel[n] / sum(per_kernel.values()), "bound": BOUND[n],
+                   "algo_bytes": ALGO_BYTES[n], "achieved_gbs": gbs}
+            if BOUND[n] == "hbm":
+                row.update({"frac": gbs / peak, "frac_nominal": gbs / NOMINAL_HBM_GBS,
+                            "traffic": tr.get("dram_bytes") if isinstance(tr, dict) else tr})
+            else:
+                # not an HBM kernel (121 taps per pixel out of shared memory): placed on the LSU roofline -- shared-memory
+                # wavefronts per launch from the committed ncu capture / (1 wavefront per clock per SM at the sampled clock)
+                wf = tr.get("smem_wavefronts") if isinstance(tr, dict) else None
+                row.update({"frac": None, "hbm_frac_for_reference_only": gbs / peak})
+                if wf:
+                    ach = wf / (per_kernel[n] * 1e-3)
+                    row.update({"achieved": ach, "peak": NUM_SMS * sm_hz, "unit": "shared-memory wavefronts/s",
+                                "frac": ach / (NUM_SMS * sm_hz), "wavefronts_per_launch": wf,
+                                "wavefronts_ideal_per_launch": tr.get("smem_wavefronts_ideal"),
+                                "source": tr.get("source")})
+            kernels.append(row)
         # the roofline object is an HBM roofline: it describes the slowest of the HBM-bound kernels; the
         # patch kernel (121 taps per pixel out of shared memory, ~9 MB of compulsory traffic per pair) is
         # listed with its share in `kernels` and cannot be placed on a bandwidth roofline meaningfully
@@ -392,24 +551,36 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "sharding": "batch (pairs) per rank, no data-path collective",
-                       "l2": "inputs larger than L2: 6.5 GB streamed per step vs 126 MB L2"},
-            "clocks": clocks.result(),
+            "config": CONFIG,
+            "clocks": clk,
             "e2e": {"value": world * B * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                    "api": "ops.build_concat_volume + ops.soft_argmin + utils.reprojection.get_reproj_error_patch"},
+                    "api": "ops.build_concat_volume + ops.soft_argmin + utils.reprojection.get_reproj_error_patch",
+                    "pipeline": "two streams: per-pair cudaMemcpyAsync of the logits overlapped with the soft-argmin of the "
+                                "pairs already on the device; D2H of the results on the copy stream",
+                    "h2d_only_ms": ms_h2d, "h2d_gbs_per_rank": h2d / (ms_h2d * 1e-3) / 1e9,
+                    "h2d_share_of_step": ms_h2d / (ms_e2e / e2e_steps),
+                    "limiter": "host->device copy of the 3.2 GB of logits per step (PCIe / host memory system; slowest rank reported)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak,
                          "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
+                         "peak_nominal": NOMINAL_HBM_GBS, "frac_nominal": dom["achieved_gbs"] / NOMINAL_HBM_GBS,
                          "selection": "slowest HBM-bound kernel of the step (see kernels[] for all shares)",
                          "hbm_bound_share_of_step": sum(k["share"] for k in kernels if k["bound"] == "hbm"),
-                         "pipeline_frac": sum(ALGO_BYTES.values()) / (ms_total / args.steps * 1e-3) / 1e9 / peak},
+                         "pipeline_frac": sum(ALGO_BYTES.values()) / (ms_total / args.steps * 1e-3) / 1e9 / peak,
+                         "pipeline_frac_nominal": sum(ALGO_BYTES.values()) / (ms_total / args.steps * 1e-3) / 1e9 / NOMINAL_HBM_GBS},
             "kernels": kernels,
             "variant_fused_upsample": {
                 "note": "informational, SURVEY §8f-1: soft-argmin fused with the trilinear upsample reads the "
                         "[B,1,48,136,240] low-res logits; not the BASELINE config, not part of value/e2e",
                 "value": world * B * args.steps / (ms_fused * 1e-3), "ms_per_step": ms_fused / args.steps,
-                "e2e_value": world * B * e2e_steps / (ms_fused_e2e * 1e-3), "h2d_bytes_per_step": h2d_fused, "unit": UNIT},
+                "e2e_value": world * B * e2e_steps / (ms_fused_e2e * 1e-3), "h2d_bytes_per_step": h2d_fused, "unit": UNIT,
+                # the fused kernel reads 64x fewer bytes than the plain soft-argmin and is bounded by the MUFU (ex2) unit:
+                # 2 ex2 per pixel and depth interval (geometric progression inside an interval) + 4 at the ends
+                "fused_soft_argmin_kernel": {
+                    "ms": ms_fused_k, "bound": "mufu", "ex2_per_launch": FUSED_EX2, "achieved": FUSED_EX2 / (ms_fused_k * 1e-3),
+                    "peak": NUM_SMS * 16 * sm_hz, "unit": "ex2/s", "frac": FUSED_EX2 / (ms_fused_k * 1e-3) / (NUM_SMS * 16 * sm_hz),
+                    "peak_source": "148 SMs x 16 MUFU lanes per clock x sampled SM clock"}},
             "loss_check": loss_val,
         }
         if not args.no_train_variant:
@@ -417,10 +588,20 @@ def run_b200(args, rank, world, local_rank):
             line["variant_train_fwd_bwd"] = {
                 "note": "informational: training hot path at the same frame size -- concat volume fwd+bwd, three "
                         "soft-argmin heads fwd+bwd, patch reprojection loss (ps=11, with Fold image) fwd+bwd; "
-                        "synthetic upstream gradients; not part of value/e2e",
+                        "synthetic upstream gradients; not part of value/e2e; rank 0's phases, slowest rank's total",
                 "value": pairs_s, "unit": UNIT, "pairs_per_gpu_per_step": TRAIN_B, "steps": TRAIN_STEPS,
                 "ms_per_step": ms_train / TRAIN_STEPS, "algo_bytes_per_pair": TRAIN_BYTES_PER_PAIR,
-                "hbm_frac": pairs_s / world * TRAIN_BYTES_PER_PAIR / 1e9 / peak}
+                "hbm_frac": pairs_s / world * TRAIN_BYTES_PER_PAIR / 1e9 / peak,
+                "hbm_frac_nominal": pairs_s / world * TRAIN_BYTES_PER_PAIR / 1e9 / NOMINAL_HBM_GBS,
+                "by_batch": {str(tb): {
+                    "ms_per_step": r_["ms_total"] / TRAIN_STEPS, "pairs_per_s_per_gpu": tb * TRAIN_STEPS / (r_["ms_total"] * 1e-3),
+                    "hbm_frac": tb * TRAIN_STEPS / (r_["ms_total"] * 1e-3) * TRAIN_BYTES_PER_PAIR / 1e9 / peak,
+                    "phases_ms": r_["phases"],
+                    "phases_hbm_frac": {n_: TRAIN_PHASE_BYTES[n_] * tb / (ms_ * 1e-3) / 1e9 / peak for n_, ms_ in r_["phases"].items()
+                                        if n_ in TRAIN_PHASE_BYTES}} for tb, r_ in train_rows.items()}}
+        if stock is not None:
+            stock["speedup_of_value_per_pair"] = (line["value"] / world) / stock["value"]
+            line["variant_stock_torch_gpu"] = stock
         if world == 1 and not args.no_cpu_baseline:
             pairs_s, _, cores = time_cpu_reference(12, 1)  # ~10 s of CPU work on the box's host cores
             line["cpu_baseline"] = {"value": pairs_s, "unit": UNIT, "cores": cores, "kind": "port",
@@ -465,6 +646,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-variant", action="store_true")
+    ap.add_argument("--no-stock-variant", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

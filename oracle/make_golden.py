@@ -209,6 +209,39 @@ def gen_reprojection_wide():
     np.savez_compressed(os.path.join(GOLDEN, "reprojection_wide.npz"), **out)
 
 
+def reprojection_720_inputs():
+    """Deterministic inputs of the 720x1280 fixture (the real IR frame size, datasets/messytable.py:325), rebuilt
+    identically by the generator and by the tests (numpy RandomState: stable across versions and machines)."""
+    rs = np.random.RandomState(720)
+    H, W = 720, 1280
+    L = (rs.rand(1, 1, H, W) > 0.5).astype(np.float32)
+    R = (rs.rand(1, 1, H, W) > 0.5).astype(np.float32)
+    xs = np.arange(W, dtype=np.float32)[None, None, None, :]
+    ys = np.arange(H, dtype=np.float32)[None, None, :, None]
+    disp = (40.0 + 28.0 * np.sin(xs / 37.0) * np.cos(ys / 53.0) + 6.0 * rs.rand(1, 1, H, W)).astype(np.float32)
+    disp[:, :, 100:140, :200] = (xs[:, :, :, :200] + 0.3)              # boundary cell x0 = -1 / 0 on the left edge
+    disp[:, :, 300:330, 900:] -= 150.0                                  # negative: samples leave on the right
+    mask = rs.rand(1, 1, H, W) > 0.25
+    return torch.from_numpy(L), torch.from_numpy(R), torch.from_numpy(np.ascontiguousarray(disp)), torch.from_numpy(mask)
+
+
+def gen_reprojection_720():
+    """get_reproj_error_patch (utils/reprojection.py:99-127) of the REAL reference on one 720x1280 frame, ps = 11.
+    The inputs are rebuilt from a seed by the test; the fixture stores the loss, strided samples of the Fold image
+    and of d loss / d disp (strides 7 x 5: every residue of the kernels' tilings is hit) and their full sums."""
+    rp, _ = ref_loader.load()
+    L, R, disp, mask = reprojection_720_inputs()
+    d = disp.clone().requires_grad_(True)
+    loss, vis, mi = rp.get_reproj_error_patch(L, R, d, mask, ps=11)
+    loss.backward()
+    g = d.grad
+    out = {"loss": _np(loss), "vis_s": _np(vis)[:, :, ::7, ::5], "gdisp_s": _np(g)[:, :, ::7, ::5],
+           "vis_sum": np.float64(_np(vis).astype(np.float64).sum()), "vis_abs_max": np.float64(_np(vis).max()),
+           "gdisp_sum": np.float64(_np(g).astype(np.float64).sum()), "gdisp_abs_sum": np.float64(np.abs(_np(g).astype(np.float64)).sum()),
+           "gdisp_abs_max": np.float64(np.abs(_np(g)).max()), "mask_sum": np.int64(_np(mi).sum())}
+    np.savez_compressed(os.path.join(GOLDEN, "reprojection_720.npz"), **out)
+
+
 def gen_scatter_warp():
     assert build_ref.build(force=True), "reference kernel source not found"
     rng = np.random.default_rng(11)
@@ -371,7 +404,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     for fn in (gen_scatter_warp, gen_temporal_ir, gen_reprojection, gen_soft_argmin, gen_psmnet_inline,
-               gen_state_dict_keys, gen_err_metrics, gen_sim_ir_pattern, gen_reprojection_wide):
+               gen_state_dict_keys, gen_err_metrics, gen_sim_ir_pattern, gen_reprojection_wide, gen_reprojection_720):
         print("generating", fn.__name__, flush=True)
         fn()
     for f in sorted(os.listdir(GOLDEN)):

@@ -246,3 +246,22 @@ def test_inter_area_restatement_matches_cv2():
         small = cv2.resize(src, (w // ks, h // ks), interpolation=cv2.INTER_AREA)
         assert np.array_equal(so.resize_area_down(src, w // ks, h // ks), small)
         assert np.array_equal(so.resize_area_up(small, w, h), cv2.resize(small, (w, h), interpolation=cv2.INTER_AREA))
+
+
+def test_reproj_patch_720x1280_fixture_is_reproducible():
+    """The 720x1280 fixture's inputs are rebuilt from a seed (oracle/make_golden.py:reprojection_720_inputs); its
+    stored outputs are the REAL reference's.  Here: the inputs are stable (checksum) and the oracle's restatement
+    reproduces the stored loss and Fold samples."""
+    import hashlib
+
+    from oracle.make_golden import reprojection_720_inputs
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reprojection_720.npz"))
+    L, R, disp, mask = reprojection_720_inputs()
+    assert L.shape == (1, 1, 720, 1280) and int(mask.sum()) == int(g["mask_sum"])
+    assert hashlib.sha1(disp.numpy().tobytes()).hexdigest() == "2c39485818e41bf5f2ec19f054190d5728f5ebb5"
+    # the whole frame through the oracle's restatement (~10 s): loss and strided Fold samples
+    dd = disp.clone().requires_grad_(True)
+    loss, vis, _ = so.reproj_error_patch(L, R, dd, mask, ps=11)
+    np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=1e-6)
+    np.testing.assert_allclose(vis[0, 0].detach().numpy()[::7, ::5], g["vis_s"][0, 0], rtol=1e-6, atol=1e-6 * float(g["vis_abs_max"]))
