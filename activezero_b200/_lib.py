@@ -58,7 +58,7 @@ SIGNATURES = {
 }
 
 # CUDA kernels enqueued by one successful call of each compute entry point
-KERNELS_PER_CALL = {"az_reproj_loss_fwd": 2, "az_temporal_ir": 3, "az_upsample_soft_argmin_bwd": 3, "az_error_metrics": 2, "az_sim_ir_pattern": 4}
+KERNELS_PER_CALL = {"az_reproj_loss_fwd": 2, "az_warp_bwd": 2, "az_bilinear_rescale_fwd": 1, "az_temporal_ir": 3, "az_upsample_soft_argmin_bwd": 3, "az_error_metrics": 2, "az_sim_ir_pattern": 4}
 
 _lib = None
 launch_count = 0    # C-ABI compute calls issued

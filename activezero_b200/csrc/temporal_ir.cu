@@ -4,88 +4,72 @@
 // (per-pixel regression over the frame stack, normalise, threshold) and
 // /root/reference/utils/reprojection.py:175-200 (local_contrast_norm).
 //
-// a11 runs in float64 like numpy (uint8 frames are promoted).  Three launches:
-//   1. slope/diff per pixel + per-image min/max (positive doubles order like uint64 => integer
-//      atomicMin/atomicMax, deterministic);
-//   2. tiled ks x ks box blur of the min-max-normalised diff with BORDER_REFLECT_101 (what
-//      cv2.blur uses by default), threshold.
-// cv2 builds the box sum with running row/column sums whose rounding differs from a direct sum at
-// the 1e-16 level; pixels whose margin to the threshold is below 1e-6 are outside the parity gate.
+// a11 (numpy promotes the uint8 frames to float64) is evaluated in EXACT integer arithmetic, see below.  Launches:
+//   1. a = |sum_t y_t (2t - (T-1))| per pixel + per-image min/max (integer atomics, deterministic);
+//   2. tiled ks x ks box sum of a with BORDER_REFLECT_101 (what cv2.blur uses by default) and the threshold test.
+// cv2 / numpy round at the 1e-16 level; pixels whose margin to the threshold is below 1e-6 are outside the parity gate.
 #include "common.cuh"
 
 namespace az {
 
-// workspace layout per image b: diff[H*W] doubles, then (after all images) minmax[2*B] as uint64 bit patterns
-__global__ void __launch_bounds__(256) tir_init_kernel(unsigned long long* __restrict__ minmax, int B) {
+// ---- exact integer form (round 2) ----------------------------------------------------------------
+// With t = 0..T-1 the reference's float64 chain (temporal_ir.py:93-114) is, in exact arithmetic,
+//   numerator = sum_t (y_t - ybar)(t - tbar) = N2 / 2,   N2 = sum_t y_t (2t - (T-1))          (an INTEGER)
+//   denominator = T (T^2 - 1) / 12,   diff = |slope (T-1)| / 255 = |N2| * 6 / (255 T (T+1))
+//   diff_n = (diff - min) / (max - min) = (a - a_min) / R,   a = |N2|,  R = a_max - a_min
+//   pattern = diff_n - boxmean_ks(diff_n) > thr   <=>   ks^2 a - boxsum_ks(a) > thr ks^2 R     (a_min cancels)
+// so the whole operator is integer sums and ONE floating-point product per image: no float64 pipe (round 1's
+// kernels spent three IEEE divisions per pixel there), 4-byte instead of 8-byte intermediates, and a result that
+// does not depend on float64 rounding at all (the reference's own 1e-16 noise only matters for pixels within
+// ~1e-13 of the threshold, far inside the 1e-6 band the parity gate excludes).
+// workspace: a[B*H*W] int32, then minmax[2*B] int32
+__global__ void __launch_bounds__(256) tir_init_kernel(int* __restrict__ minmax, int B) {
     const int t = blockIdx.x * 256 + threadIdx.x;
     if (t < B) {
-        minmax[2 * t] = 0x7FF0000000000000ull;  // +inf
-        minmax[2 * t + 1] = 0ull;               // +0.0
+        minmax[2 * t] = 0x7fffffff;
+        minmax[2 * t + 1] = 0;
     }
 }
 
+// grid = (ceil(H*W/V/256), B); a thread owns V adjacent pixels (V = 4: one 32-bit load per frame, one 128-bit store)
 template <int V>
-__device__ __forceinline__ void tir_load(const uint8_t* __restrict__ f, double* y) {
-    if (V == 4) {
-        const uchar4 q = *reinterpret_cast<const uchar4*>(f);
-        y[0] = (double)q.x; y[1 % V] = (double)q.y; y[2 % V] = (double)q.z; y[3 % V] = (double)q.w;
-    } else {
-        y[0] = (double)f[0];
-    }
-}
-
-// grid = (ceil(H*W/V/256), B); a thread owns V adjacent pixels (V = 4: one 32-bit load per frame).
-// temporal_ir.py:94-107, numpy float64 op order (no FMA contraction); the frames are read twice (mean,
-// then centred products) -- the second pass hits L1/L2.
-template <int V>
-__global__ void __launch_bounds__(256) tir_slope_kernel(const uint8_t* __restrict__ frames, double* __restrict__ diff,
-                                                        unsigned long long* __restrict__ minmax, int T, int64_t HW) {
+__global__ void __launch_bounds__(256) tir_slope_kernel(const uint8_t* __restrict__ frames, int* __restrict__ aout,
+                                                        int* __restrict__ minmax, int T, int64_t HW) {
     const int64_t p = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V;
     const int b = blockIdx.y;
-    const bool on = p < HW;
-    const double t_avg = (double)((T - 1) * T / 2) / (double)T;  // np.average of the int ramp
-    double mn = __longlong_as_double(0x7FF0000000000000ll), mx = 0.0;
-    if (on) {
+    int mn = 0x7fffffff, mx = 0;
+    if (p < HW) {
         const uint8_t* f = frames + (size_t)b * T * HW + p;
-        double ysum[V], y[V], num[V], y_avg[V];
+        int acc[V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) { ysum[j] = 0.0; num[j] = 0.0; }
+        for (int j = 0; j < V; ++j) acc[j] = 0;
         for (int t = 0; t < T; ++t) {
-            tir_load<V>(f + (size_t)t * HW, y);
-#pragma unroll
-            for (int j = 0; j < V; ++j) ysum[j] += y[j];  // exact (integers)
-        }
-#pragma unroll
-        for (int j = 0; j < V; ++j) y_avg[j] = ysum[j] / (double)T;
-        double den = 0.0;
-        for (int t = 0; t < T; ++t) {
-            const double dt = (double)t - t_avg;
-            den = __dadd_rn(den, __dmul_rn(dt, dt));
-            tir_load<V>(f + (size_t)t * HW, y);
-#pragma unroll
-            for (int j = 0; j < V; ++j) num[j] = __dadd_rn(num[j], __dmul_rn(y[j] - y_avg[j], dt));
+            const int wgt = 2 * t - (T - 1);
+            if (V == 4) {
+                const uchar4 q = *reinterpret_cast<const uchar4*>(f + (size_t)t * HW);
+                acc[0] += wgt * (int)q.x; acc[1 % V] += wgt * (int)q.y; acc[2 % V] += wgt * (int)q.z; acc[3 % V] += wgt * (int)q.w;
+            } else {
+                acc[0] += wgt * (int)f[(size_t)t * HW];
+            }
         }
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            const double slope = num[j] / den;
-            const double icpt = __dsub_rn(y_avg[j], __dmul_rn(slope, t_avg));
-            const double first = __dadd_rn(__dmul_rn(slope, 0.0), icpt);
-            const double last = __dadd_rn(__dmul_rn(slope, (double)(T - 1)), icpt);
-            const double v = fabs(__dsub_rn(last, first) / 255.0);  // :110-111
-            diff[(size_t)b * HW + p + j] = v;
-            mn = fmin(mn, v);
-            mx = fmax(mx, v);
+            acc[j] = abs(acc[j]);
+            mn = min(mn, acc[j]);
+            mx = max(mx, acc[j]);
         }
+        int* o = aout + (size_t)b * HW + p;
+        if (V == 4) *reinterpret_cast<int4*>(o) = make_int4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
+        else o[0] = acc[0];
     }
-    // block min / max, then one integer atomic each
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicMin(&minmax[2 * b], (unsigned long long)__double_as_longlong(mn));
-        atomicMax(&minmax[2 * b + 1], (unsigned long long)__double_as_longlong(mx));
+        atomicMin(&minmax[2 * b], mn);
+        atomicMax(&minmax[2 * b + 1], mx);
     }
 }
 
@@ -101,39 +85,36 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 constexpr int kTirTX = 32, kTirTY = 8;  // tile of the generic LCN fallback below
 
-// Box blur + threshold.  grid = (ceil(W/64), ceil(H/32), B), 256 threads; separable sliding-window sums:
-//   smem tile (32+ks-1) x (64+ks-1) normalised values (one float64 division per tile element, 1.5x the
-//   image instead of the 3x of a 32x8 tile), then horizontal window sums for runs of 8 outputs per thread,
-//   then vertical window sums for runs of 8 rows per thread.
+// Box sum + threshold.  grid = (ceil(W/64), ceil(H/32), B), 256 threads; separable sliding-window INTEGER sums:
+//   smem tile (32+ks-1) x (64+ks-1) of a (BORDER_REFLECT_101, what cv2.blur uses by default), horizontal window
+//   sums for runs of 8 outputs per thread, vertical window sums for runs of 8 rows per thread, then the test
+//   ks^2 a - boxsum > thr ks^2 R  (left side exact in int64, right side one double product per image).
 constexpr int kTpTW = 64, kTpTH = 32;
 
-__global__ void __launch_bounds__(256) tir_pattern_kernel(const double* __restrict__ diff,
-                                                          const unsigned long long* __restrict__ minmax,
+__global__ void __launch_bounds__(256) tir_pattern_kernel(const int* __restrict__ ain, const int* __restrict__ minmax,
                                                           float* __restrict__ pattern, int H, int W, int ks,
                                                           double threshold) {
-    extern __shared__ double tile[];
+    extern __shared__ int itile[];
     const int h = ks >> 1;
     const int IW = kTpTW + ks - 1, IH = kTpTH + ks - 1;
-    double* rows = tile + IW * IH;  // [IH][TW] horizontal window sums
+    int* rows = itile + IW * IH;  // [IH][TW] horizontal window sums
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH;
-    const double mn = __longlong_as_double((long long)minmax[2 * b]);
-    const double mx = __longlong_as_double((long long)minmax[2 * b + 1]);
-    const double range = __dsub_rn(mx, mn);
-    const double* d = diff + (size_t)b * H * W;
+    const double rhs = threshold * (double)(ks * ks) * (double)(minmax[2 * b + 1] - minmax[2 * b]);
+    const int* d = ain + (size_t)b * H * W;
     const int tid = threadIdx.x;
     for (int t = tid; t < IW * IH; t += 256) {
         const int ty = t / IW, tx = t - ty * IW;
         const int yy = reflect101(y0 + ty - h, H), xx = reflect101(x0 + tx - h, W);
-        tile[t] = fabs(__dsub_rn(d[(size_t)yy * W + xx], mn) / range);  // :113 normalise, :36 abs
+        itile[t] = __ldg(d + (size_t)yy * W + xx);
     }
     __syncthreads();
     for (int it = tid; it < IH * (kTpTW / 8); it += 256) {
         const int ty = it / (kTpTW / 8), xl = 8 * (it - ty * (kTpTW / 8));
-        const double* r = tile + ty * IW + xl;
-        double s = 0.0;
+        const int* r = itile + ty * IW + xl;
+        int s = 0;
         for (int k = 0; k < ks; ++k) s += r[k];
-        double* o = rows + ty * kTpTW + xl;
+        int* o = rows + ty * kTpTW + xl;
         o[0] = s;
 #pragma unroll
         for (int j = 1; j < 8; ++j) {
@@ -145,16 +126,15 @@ __global__ void __launch_bounds__(256) tir_pattern_kernel(const double* __restri
     const int c = tid & (kTpTW - 1), r0 = (tid / kTpTW) * 8;
     const int x = x0 + c;
     if (x >= W) return;
-    double s = 0.0;
+    long long s = 0;
     for (int k = 0; k < ks; ++k) s += rows[(r0 + k) * kTpTW + c];
-    const double inv = 1.0 / (double)(ks * ks);
+    const long long k2 = (long long)ks * ks;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int y = y0 + r0 + r;
         if (y < H) {
-            const double blur = __dmul_rn(s, inv);
-            const double v = tile[(r0 + r + h) * IW + c + h];
-            pattern[(size_t)b * H * W + (size_t)y * W + x] = (__dsub_rn(v, blur) > threshold) ? 1.0f : 0.0f;
+            const long long lhs = k2 * (long long)itile[(r0 + r + h) * IW + c + h] - s;
+            pattern[(size_t)b * H * W + (size_t)y * W + x] = ((double)lhs > rhs) ? 1.0f : 0.0f;
         }
         if (r < 7) s += rows[(r0 + r + ks) * kTpTW + c] - rows[(r0 + r) * kTpTW + c];
     }
@@ -302,21 +282,21 @@ static int launch_lcn_sep(const float* image, float* normed, float* stdo, int B,
 using namespace az;
 
 extern "C" int64_t az_temporal_ir_workspace_bytes(int64_t B, int64_t H, int64_t W) {
-    return (B * H * W + 2 * B) * (int64_t)sizeof(double);
+    return (B * H * W + 2 * B) * (int64_t)sizeof(int);
 }
 
 extern "C" int az_temporal_ir(const uint8_t* frames, float* pattern, void* workspace, int64_t B, int64_t T, int64_t H,
                               int64_t W, int64_t ks, double threshold, void* stream) {
     if (!frames || !pattern || !workspace || B <= 0 || T < 2 || H <= 0 || W <= 0 || ks < 1 || (ks % 2) == 0)
         return AZ_ERR_BAD_ARG;
-    if (B > 65535 || H * W >= (1ll << 31) || ks > 63) return AZ_ERR_BAD_ARG;
+    if (B > 65535 || H * W >= (1ll << 31) || ks > 63 || T > 4096) return AZ_ERR_BAD_ARG;  // |N2| <= 255 T^2 / 2 fits int32
     cudaStream_t st = (cudaStream_t)stream;
-    double* diff = (double*)workspace;
-    unsigned long long* minmax = (unsigned long long*)(diff + B * H * W);
+    int* diff = (int*)workspace;
+    int* minmax = diff + B * H * W;
     const int64_t HW = H * W;
     tir_init_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(minmax, (int)B);
     AZ_LAUNCH_CHECK();
-    if (HW % 4 == 0 && (reinterpret_cast<uintptr_t>(frames) & 3u) == 0) {
+    if (HW % 4 == 0 && (reinterpret_cast<uintptr_t>(frames) & 3u) == 0 && aligned16(workspace)) {
         dim3 g1((unsigned)ceil_div(HW / 4, 256), (unsigned)B);
         tir_slope_kernel<4><<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
     } else {
@@ -325,7 +305,7 @@ extern "C" int az_temporal_ir(const uint8_t* frames, float* pattern, void* works
     }
     AZ_LAUNCH_CHECK();
     const int IW = kTpTW + (int)ks - 1, IH = kTpTH + (int)ks - 1;
-    const size_t smem = ((size_t)IW * IH + (size_t)IH * kTpTW) * sizeof(double);
+    const size_t smem = ((size_t)IW * IH + (size_t)IH * kTpTW) * sizeof(int);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(tir_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256, 4) reproj_ps1_kernel(const float* __restr
     }
 }
 
-// a6 backward.  gdisp written; gimg accumulated with atomics (zero-filled by the caller).
+// a6 backward w.r.t. the disparity (gimg != nullptr: round 1's atomic image gradient, kept for AZ_WARP_BWD_IMG=0).
 __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__ img, const float* __restrict__ disp,
                                                        const float* __restrict__ lin_x,
                                                        const float* __restrict__ lin_y,
@@ -212,6 +212,86 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__
         // chain of grid_sample's unnormalise (x W/2), `2*flow-1` (x 2) and `disp/width` (/ W)
         gdisp[(size_t)b * HW + pix] = ((gix * (0.5f * (float)W)) * 2.0f) / (float)W;
     }
+}
+
+
+// a6 backward w.r.t. the IMAGE, deterministic (round 2; torch's grid_sampler_2d_backward and round 1's kernel use
+// float atomics, whose summation order changes from run to run).  One CTA owns one image row y' of one (b, c):
+// ys depends on the output row only and grows by H/(H-1) per row, so y' is a bilinear corner of at most three
+// output rows i (y0(i) in {y'-1, y'}); the threads walk those rows and add every output pixel's two horizontal
+// corner contributions into a shared row of 64-bit FIXED-POINT accumulators (integer addition is associative:
+// the result does not depend on the order of the atomics), scaled per row so that the worst case -- every pixel of
+// the three rows landing on one column -- cannot overflow.  The row is then converted and STORED: every element
+// of gimg is written exactly once, no zero-fill by the caller, no global atomics.
+// grid = (H, C, B), 256 threads, dynamic smem = W * 8 bytes.
+__global__ void __launch_bounds__(256) warp_bwd_img_kernel(const float* __restrict__ disp,
+                                                           const float* __restrict__ lin_x,
+                                                           const float* __restrict__ lin_y,
+                                                           const float* __restrict__ gout, float* __restrict__ gimg,
+                                                           int C, int H, int W) {
+    extern __shared__ unsigned long long facc[];
+    __shared__ float red[8];
+    __shared__ int rows_s[4];
+    __shared__ float wts_s[4];
+    const int yp = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const size_t HW = (size_t)H * W;
+    const float* gplane = gout + ((size_t)b * C + c) * HW;
+    const float* dplane = disp + (size_t)b * HW;
+    for (int x = tid; x < W; x += 256) facc[x] = 0ull;
+    if (tid == 0) {
+        int n = 0;
+        for (int i = max(yp - 2, 0); i <= min(yp + 2, H - 1); ++i) {
+            const Axis ay = make_axis(sample_pos(__ldg(lin_y + i), 0.0f, (float)H), H);
+            float wy = 0.f;
+            if (ay.v0 && ay.i0 == yp) wy += ay.e;
+            if (ay.v1 && ay.i0 + 1 == yp) wy += ay.w;
+            if (wy != 0.f && n < 4) {
+                rows_s[n] = i;
+                wts_s[n] = wy;
+                ++n;
+            }
+        }
+        for (; n < 4; ++n) rows_s[n] = -1;
+    }
+    __syncthreads();
+    // scale: 2^61 / (sum over the candidate rows of W * max |wy * g|)
+    float m = 0.f;
+    for (int r = 0; r < 4; ++r) {
+        const int i = rows_s[r];
+        if (i < 0) continue;
+        const float wy = wts_s[r];
+        for (int j = tid; j < W; j += 256) m = fmaxf(m, fabsf(wy * __ldg(gplane + (size_t)i * W + j)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) m = fmaxf(m, red[k]);
+    float* orow = gimg + ((size_t)b * C + c) * HW + (size_t)yp * W;
+    if (m == 0.f || !(m < 3.0e38f)) {  // all-zero upstream gradient, or a non-finite one (propagated as NaN)
+        const float fill = (m == 0.f) ? 0.f : __int_as_float(0x7fc00000);
+        for (int x = tid; x < W; x += 256) orow[x] = fill;
+        return;
+    }
+    const double scale = ldexp(1.0, 61) / ((double)m * 4.0 * (double)W);
+    for (int r = 0; r < 4; ++r) {
+        const int i = rows_s[r];
+        if (i < 0) continue;
+        const float wy = wts_s[r];
+        for (int j = tid; j < W; j += 256) {
+            const float d = __ldg(dplane + (size_t)i * W + j);
+            const Axis ax = make_axis(sample_pos(__ldg(lin_x + j), __fdiv_rn(d, (float)W), (float)W), W);
+            const float g = wy * __ldg(gplane + (size_t)i * W + j);
+            if (ax.v0) atomicAdd(&facc[ax.i0], (unsigned long long)__double2ll_rn((double)(ax.e * g) * scale));
+            if (ax.v1) atomicAdd(&facc[ax.i0 + 1], (unsigned long long)__double2ll_rn((double)(ax.w * g) * scale));
+        }
+    }
+    __syncthreads();
+    const double inv = 1.0 / scale;
+    for (int x = tid; x < W; x += 256) orow[x] = (float)((double)(long long)facc[x] * inv);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -553,10 +633,28 @@ extern "C" int az_warp_bwd(const float* img, const float* disp, const float* lin
     if (!img || !disp || !lin_x || !lin_y || !gout || B <= 0 || C <= 0 || H <= 0 || W <= 0) return AZ_ERR_BAD_ARG;
     if (H > 65535 || B > 65535 || H * W >= (1ll << 31)) return AZ_ERR_BAD_ARG;
     if (!gimg && !gdisp) return 0;
-    dim3 grid((unsigned)ceil_div(W, 256), (unsigned)H, (unsigned)B);
-    warp_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, disp, lin_x, lin_y, gout, gimg, gdisp, (int)C, (int)H,
-                                                           (int)W);
-    AZ_LAUNCH_CHECK();
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool det_img = gimg != nullptr && tuning("AZ_WARP_BWD_IMG", 1) == 1 && C <= 65535 && W * 8 <= 200 * 1024;
+    if (gimg != nullptr && !det_img) {  // round 1's float-atomic path accumulates: it needs zeros to start from
+        cudaError_t e = cudaMemsetAsync(gimg, 0, (size_t)B * C * H * W * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (gdisp != nullptr || (gimg != nullptr && !det_img)) {
+        dim3 grid((unsigned)ceil_div(W, 256), (unsigned)H, (unsigned)B);
+        warp_bwd_kernel<<<grid, 256, 0, st>>>(img, disp, lin_x, lin_y, gout, det_img ? nullptr : gimg, gdisp, (int)C, (int)H,
+                                              (int)W);
+        AZ_LAUNCH_CHECK();
+    }
+    if (det_img) {
+        const size_t smem = (size_t)W * 8;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(warp_bwd_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        dim3 grid((unsigned)H, (unsigned)C, (unsigned)B);
+        warp_bwd_img_kernel<<<grid, 256, smem, st>>>(disp, lin_x, lin_y, gout, gimg, (int)C, (int)H, (int)W);
+        AZ_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -285,7 +285,7 @@ class WarpFn(torch.autograd.Function):
         im, d = ctx.saved_tensors
         B, C, H, W = im.shape
         g = _cuda_f32(gout, "grad_out")
-        gimg = torch.zeros_like(im) if ctx.needs_input_grad[0] else None
+        gimg = torch.empty_like(im) if ctx.needs_input_grad[0] else None  # fully written by the kernel
         gdisp = torch.empty_like(d) if ctx.needs_input_grad[1] else None
         lx, ly = linspace_table(W, im.device), linspace_table(H, im.device)
         with torch.cuda.device(im.device):

@@ -112,6 +112,7 @@ def main():
                     help="emit the cost volume in channels_last_3d (SURVEY 8f rank 2, layout clause)")
     ap.add_argument("--fuse-upsample", action="store_true",
                     help="use the fused trilinear-upsample + soft-argmin kernel for the three heads (SURVEY §8f-1)")
+    ap.add_argument("--profile", action="store_true", help="after the timed region: kernel-time shares via torch.profiler")
     args = ap.parse_args()
 
     rank, world, local = dist_util.env_rank_world()
@@ -154,6 +155,34 @@ def main():
     dist_util.barrier()
     torch.cuda.synchronize()
     (ms,) = dist_util.max_over_ranks([start.elapsed_time(stop)], dev)
+
+    # where the device time goes (rank 0, two more iterations under torch.profiler / CUPTI): this library's kernels
+    # (the hot path), NCCL (DDP's gradient all-reduce: 2 x 20.9 MB per iteration) and everything else
+    # (cuDNN / torch).  A number measured under the profiler is not a throughput; only the SHARES are reported.
+    shares = None
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+
+        dist_util.barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                one_iteration()
+            torch.cuda.synchronize()
+        az = nccl = other = 0.0
+        for e in prof.key_averages():
+            t = float(getattr(e, "device_time_total", 0.0) or getattr(e, "cuda_time_total", 0.0))
+            name = e.key
+            if "az::" in name or name.startswith("void az") or "az_" in name:
+                az += t
+            elif "nccl" in name.lower():
+                nccl += t
+            else:
+                other += t
+        tot = az + nccl + other
+        shares = {"hot_path_kernels_ms_per_iter": az / 2e3, "nccl_ms_per_iter": nccl / 2e3, "other_ms_per_iter": other / 2e3,
+                  "hot_path_share_of_kernel_time": az / tot if tot else None, "nccl_share_of_kernel_time": nccl / tot if tot else None,
+                  "note": "kernel time summed over streams (NCCL overlaps the backward): nccl_ms is its busy time, the EXPOSED "
+                          "part is what the iteration time grows by from 1 GPU to N (see the efficiency table)"}
     if rank == 0:
         print(json.dumps({
             "metric": "training pairs/s (sim step + real step per iteration)" if not args.no_real else "training pairs/s (sim step)",
@@ -163,6 +192,7 @@ def main():
                                    f"D={MAX_DISP}, batch {args.batch}/GPU, patch reproj ps={PATCH}, T={args.frames}",
                        "ddp": world > 1, "fuse_upsample": args.fuse_upsample,
                        "channels_last_3d": args.channels_last_3d},
+            "device_time_shares_rank0": shares,
             "final_loss": float(last)}), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -93,8 +93,9 @@ int az_upsample_soft_argmin_bwd(const float* lowres, const float* disp, const fl
  * img,out: [B,C,H,W]; disp: [B,1,H,W] (already signed: the reference passes -pred_disp_l). */
 int az_warp_fwd(const float* img, const float* disp, const float* lin_x, const float* lin_y, float* out,
                 int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
-/* gdisp [B,1,H,W] (may be NULL) is written; gimg [B,C,H,W] (may be NULL) must be zero-filled by the
- * caller and is accumulated with float atomics (as torch's grid_sampler backward does). */
+/* gdisp [B,1,H,W] and gimg [B,C,H,W] (each may be NULL) are fully WRITTEN (no zero-fill by the caller).  The image
+ * gradient is a deterministic gather per image row with order-independent fixed-point accumulation; torch's
+ * grid_sampler backward uses float atomics. */
 int az_warp_bwd(const float* img, const float* disp, const float* lin_x, const float* lin_y,
                 const float* gout, float* gimg, float* gdisp,
                 int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
@@ -150,7 +151,8 @@ int az_scatter_warp(const float* src, const int32_t* disp, float* dst, int32_t* 
 /* ---- a11: temporal IR pattern -- tools/temporal_ir.py:35-40, 93-114 ----
  * frames: [B,T,H,W] uint8 -> pattern [B,H,W] float32 in {0,1}: per-pixel least-squares slope over t,
  * |fit[T-1]-fit[0]|/255, per-image min-max normalise, minus ks x ks box blur (BORDER_REFLECT_101),
- * > threshold.  float64 arithmetic as numpy.  workspace: az_temporal_ir_workspace_bytes(B,H,W) bytes. */
+ * > threshold.  Evaluated in exact integer arithmetic (the reference's float64 chain reduces to integer sums and one
+ * comparison, csrc/temporal_ir.cu); T <= 4096.  workspace: az_temporal_ir_workspace_bytes(B,H,W) bytes, 16-byte aligned. */
 int64_t az_temporal_ir_workspace_bytes(int64_t B, int64_t H, int64_t W);
 int az_temporal_ir(const uint8_t* frames, float* pattern, void* workspace,
                    int64_t B, int64_t T, int64_t H, int64_t W, int64_t ks, double threshold, void* stream);

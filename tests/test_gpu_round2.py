@@ -366,3 +366,51 @@ def test_patch_real_reference_720x1280(golden, impl):
     assert bool(((gs - ref).abs() <= 1e-5 * ref.abs() + 1e-5 * gmax).all())
     assert abs(float(vis.double().sum()) - float(g["vis_sum"])) <= 1e-6 * float(g["vis_sum"])
     assert abs(float(d.grad.double().abs().sum()) - float(g["gdisp_abs_sum"])) <= 1e-5 * float(g["gdisp_abs_sum"])
+
+
+# --------------------------------------------------------------------------- a6 backward: deterministic image gradient
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 3, 24, 40), (1, 1, 17, 133), (1, 2, 64, 256)])
+def test_warp_image_gradient_matches_autograd(impl, shape):
+    """d out / d img of apply_disparity (reprojection.py:13-35) against fp64 autograd of the oracle; impl = 1 is the
+    round-2 gather kernel (order-independent fixed-point sums: bit-identical from run to run, gimg fully written),
+    impl = 0 round 1's float atomics."""
+    torch.manual_seed(17)
+    B, C, H, W = shape
+    img = torch.randn(shape, dtype=torch.float64, requires_grad=True)
+    d = (torch.rand(B, 1, H, W, dtype=torch.float64) - 0.3) * 0.6 * W  # both borders are crossed
+    d.requires_grad_(True)
+    g = torch.randn(shape, dtype=torch.float64)
+    so.apply_disparity(img, d).backward(g)
+    with _env(AZ_WARP_BWD_IMG=impl):
+        grads = []
+        for _ in range(2):
+            ig = img.detach().float().to(DEV).requires_grad_(True)
+            dg = d.detach().float().to(DEV).requires_grad_(True)
+            ops.warp(ig, dg).backward(g.float().to(DEV))
+            torch.cuda.synchronize()
+            grads.append((ig.grad.clone(), dg.grad.clone()))
+    close(grads[0][0], img.grad, rtol=1e-5, floor=1e-5)
+    close(grads[0][1], d.grad, rtol=1e-4, floor=1e-4)  # fp32 sample positions: the disparity gradient jumps at integer positions
+    if impl == 1:
+        assert torch.equal(grads[0][0], grads[1][0])
+
+
+def test_warp_image_gradient_degenerate_upstream():
+    img = torch.randn(1, 1, 8, 16, device=DEV, requires_grad=True)
+    d = torch.rand(1, 1, 8, 16, device=DEV) * 4
+    ops.warp(img, d).backward(torch.zeros(1, 1, 8, 16, device=DEV))
+    assert float(img.grad.abs().max()) == 0.0
+
+
+def test_temporal_ir_integer_form_is_exact_on_ties_free_input():
+    """The integer evaluation of tools/temporal_ir.py:93-114 against the oracle's float64 restatement: identical
+    patterns (the two can only differ within float64 rounding of the threshold), several T, ks and a constant image."""
+    rs = np.random.RandomState(3)
+    for T_, H, W, ks in [(7, 90, 130, 11), (4, 64, 64, 11), (12, 40, 57, 5), (2, 33, 20, 3)]:
+        fr = rs.randint(0, 256, (T_, H, W)).astype(np.uint8)
+        ref = so.temporal_ir_pattern(fr, ks=ks, threshold=0.005)
+        out = ops.temporal_ir_pattern(torch.from_numpy(fr).to(DEV), ks=ks, threshold=0.005).cpu().numpy()
+        assert float((out != ref).mean()) <= 1e-5, (T_, H, W, ks)
+    const = torch.full((7, 32, 32), 9, dtype=torch.uint8, device=DEV)
+    assert float(ops.temporal_ir_pattern(const).abs().max()) == 0.0  # the reference divides 0/0 here: NaN > thr is False
