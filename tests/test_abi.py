@@ -37,7 +37,7 @@ def test_library_loads_through_binding(lib_path):
     assert lib.az_version().decode().endswith("sm_100a")
     assert b"bad argument" in lib.az_error_string(-1)
     assert _lib.query("az_reproj_workspace_bytes", 2, 10) == 2 * 10 * 16
-    assert _lib.query("az_temporal_ir_workspace_bytes", 2, 4, 5) == (2 * 4 * 5 + 4) * 8
+    assert _lib.query("az_temporal_ir_workspace_bytes", 2, 4, 5) == (2 * 4 * 5 + 4) * 4  # int32 since round 2 (integer form)
 
 
 def test_library_is_sm100a_only(lib_path):
