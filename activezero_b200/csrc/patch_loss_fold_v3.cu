@@ -89,7 +89,9 @@ struct Args {
     int nbuf;       // 1 or 2 buffers for the blended rows / parameters
     int vec;        // W % 4 == 0 and every image pointer 16-byte aligned
     int PR, PL, PV; // row pitches (in 8-byte elements) of Rs, Ls, Vacc; PR/2, PL/2, PV/2 odd
-    int GT;         // groups per row incl. padding = 16 n NW
+    int GT;         // groups per x-tile incl. padding = 16 n NW
+    int ntile;      // x-tiles per row (1 unless the row does not fit: W > ~1400 at ps = 11); a tile is 4 GT sources
+    int sb_rows;    // rows of the tile-boundary side buffer = band_rows + 2p
 };
 
 template <int PS>
@@ -105,7 +107,7 @@ struct Geom {
 
 __device__ __forceinline__ float4 load4(const float* __restrict__ img, int y, int x, int H, int W, bool vec) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y >= 0 && y < H && x < W) {
+    if (y >= 0 && y < H && x >= 0 && x < W) {
         const float* p = img + (size_t)y * W + x;
         if (vec) {
             v = __ldg(reinterpret_cast<const float4*>(p));
@@ -123,7 +125,7 @@ __device__ __forceinline__ float4 load4(const float* __restrict__ img, int y, in
 template <int PS>
 __device__ __forceinline__ void stage_row(const Args& a, const float* __restrict__ sp, const float* __restrict__ tp,
                                           const float* __restrict__ dimg, const uint8_t* __restrict__ mimg, int i,
-                                          int buf, bool first, uint32_t sRs, uint32_t sLs, float* PsW, int* PsC) {
+                                          int X0, int buf, bool first, uint32_t sRs, uint32_t sLs, float* PsW, int* PsC) {
     using T = Geom<PS>;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int H = a.H, W = a.W;
@@ -161,7 +163,7 @@ __device__ __forceinline__ void stage_row(const Args& a, const float* __restrict
     const int tid2 = nthreads - 1 - tid;
     const int gq = a.GT;  // quads incl. padding groups: their sources are invalid
     for (int m = tid2; m < gq; m += nthreads) {
-        const int x = 4 * m;
+        const int xl = 4 * m, x = X0 + xl;  // tile-local / image column of the quad
         const float4 d4 = load4(dimg, i, x, H, W, vec);
         const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
         uint32_t m4 = 0x01010101u;
@@ -194,25 +196,27 @@ __device__ __forceinline__ void stage_row(const Args& a, const float* __restrict
             cc[t] = (base << 3) | msk | flags;
             ww[t] = wx;
         }
-        *reinterpret_cast<int4*>(PsC + buf * 4 * a.GT + x) = make_int4(cc[0], cc[1], cc[2], cc[3]);
-        *reinterpret_cast<float4*>(PsW + buf * 4 * a.GT + x) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+        *reinterpret_cast<int4*>(PsC + buf * 4 * a.GT + xl) = make_int4(cc[0], cc[1], cc[2], cc[3]);
+        *reinterpret_cast<float4*>(PsW + buf * 4 * a.GT + xl) = make_float4(ww[0], ww[1], ww[2], ww[3]);
     }
 
-    // (3) the target row pair(s) entering the ring: Ls[slot][P + x] = (row y, row y + 1), y = 2 pid - YB
+    // (3) the target row pair(s) entering the ring: Ls[slot][P + xl] = (row y, row y + 1), y = 2 pid - YB, for the
+    //     tile-local columns xl in [-p, 4 GT + p) (image columns X0 + xl; zero outside the image)
     const int np_new = first ? T::NP : (e0 == 0 ? 1 : 0);  // a new pair enters when e0 flips to 0
     for (int nn = 0; nn < np_new; ++nn) {
         const int pid = first ? pid0 + nn : pid0 + T::NP - 1;
         const int y = 2 * pid - T::YB;
-        const uint32_t rowb = sLs + ((uint32_t)(pid % T::RING) * (uint32_t)a.PL + (uint32_t)T::P) * 8u;
-        for (int m = tid2; m < nq; m += nthreads) {
-            const int x = 4 * m;
-            const float4 u = load4(tp, y, x, H, W, vec);
-            const float4 v = load4(tp, y + 1, x, H, W, vec);
-            const uint32_t d = rowb + (uint32_t)x * 8u;
-            sts64(d, u.x, v.x);
-            sts64(d + 8u, u.y, v.y);
-            sts64(d + 16u, u.z, v.z);
-            sts64(d + 24u, u.w, v.w);
+        const uint32_t rowb = sLs + ((uint32_t)(pid % T::RING) * (uint32_t)a.PL) * 8u;
+        for (int m = tid2; m < a.GT + 4; m += nthreads) {
+            const int xl = 4 * (m - 2);
+            const float4 u = load4(tp, y, X0 + xl, H, W, vec);
+            const float4 v = load4(tp, y + 1, X0 + xl, H, W, vec);
+            const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int idx = xl + t + T::P;
+                if (idx >= 0 && idx < a.PL) sts64(rowb + (uint32_t)idx * 8u, uu[t], vv[t]);
+            }
         }
     }
 }
@@ -268,6 +272,53 @@ __device__ __forceinline__ void walk_group(const int (&code)[4], const float (&w
     }
 }
 
+
+// Writes Fold row y of x-tile `xt` to HBM from ring slot `vrow_f` (floats; + half selects the row of the pair).
+// Column x (tile-local xl = x - X0) sums, in a fixed order, the private strips that cover it: the strip to the left
+// (its right overhang), its own, the strip to the right (its left overhang).  Between x-tiles the 2p columns
+// around the seam are handed over through the side buffer SB: tile t keeps them (their sums over its own sources)
+// instead of emitting its last p columns, tile t+1 adds them to its own share and emits columns [X0 - p, ...).
+// Every element of the image is therefore written once per CTA (rows shared with the neighbouring band: one atomic
+// add per CTA onto zero-filled memory, two addends).
+template <int PS>
+__device__ __forceinline__ void emit_row(const Args& a, float* __restrict__ vslot, int half, bool recycle,
+                                         const float* __restrict__ sb_in, float* __restrict__ sb_out,
+                                         float* __restrict__ vimg_row, bool shared_row, bool store, int xt, int X0,
+                                         int RWd) {
+    using T = Geom<PS>;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int SW = 64 * a.n, TW = 4 * a.GT, W = a.W;
+    const bool last = xt + 1 == a.ntile;
+    const float* vr = vslot + half;
+    const float2 z2 = make_float2(0.f, 0.f);
+    // tile-local columns [-p, TW + p): every entry of the slot is read (and, when the slot is recycled, cleared) by
+    // exactly one thread -- no barrier between the reads and the clears
+    for (int xl = tid - T::P; xl < TW + T::P; xl += nthreads) {
+        const int w0 = min(max(xl, 0) / SW, a.NW - 1), xw = xl - w0 * SW;  // xw in [-p, SW + p)
+        const int li = w0 * RWd + xw + T::P;
+        const bool from_left = xw < T::P && w0 > 0;                       // right overhang of the strip to the left
+        const bool from_right = xw >= SW - T::P && xw < SW && w0 + 1 < a.NW;  // left overhang of the strip to the right
+        float v = 0.f;
+        if (xt > 0 && xl < T::P) v += sb_in[xl + T::P];  // the previous tile's share of the seam columns
+        if (from_left) v += vr[2 * (li - RWd + SW)];
+        v += vr[2 * li];
+        if (from_right) v += vr[2 * (li + RWd - SW)];
+        if (recycle) {
+            if (from_left) *reinterpret_cast<float2*>(vslot + 2 * (li - RWd + SW)) = z2;
+            *reinterpret_cast<float2*>(vslot + 2 * li) = z2;
+            if (from_right) *reinterpret_cast<float2*>(vslot + 2 * (li + RWd - SW)) = z2;
+        }
+        const int x = X0 + xl;
+        if (!last && xl >= TW - T::P) {
+            sb_out[xl - (TW - T::P)] = v;  // seam: handed to the next tile (the other half of the double buffer)
+        } else if (store && x >= 0 && x < W) {
+            float* op = vimg_row + x;
+            if (shared_row) atomicAdd(op, v);
+            else *op = v;
+        }
+    }
+}
+
 constexpr int kMaxThreads = 480;  // 15 warps: 136 registers per thread (the walk keeps ~90 live packed values)
 
 template <int PS, bool GRAD>
@@ -293,6 +344,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) patch_loss_fold_v3_kernel(cons
     float* PsW = Vacc + (size_t)2 * T::RING * a.PV;                  // [nbuf][4 GT] horizontal weight of each source
     int* PsC = reinterpret_cast<int*>(PsW + (size_t)a.nbuf * 4 * a.GT);  // [nbuf][4 GT] window start << 3 | mask << 2 | edge flags
     const int total_floats = 2 * a.nbuf * rsBuf + 2 * T::RING * a.PL + 2 * T::RING * a.PV + 2 * a.nbuf * 4 * a.GT;
+    float* SB = sm + total_floats;                                   // [2][sb_rows][2p] sums handed from x-tile t to t+1 (double buffer)
     const uint32_t sRs = (uint32_t)__cvta_generic_to_shared(Rs);
     const uint32_t sLs = (uint32_t)__cvta_generic_to_shared(Ls);
     const uint32_t sV = (uint32_t)__cvta_generic_to_shared(Vacc);
@@ -311,17 +363,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) patch_loss_fold_v3_kernel(cons
         const float* sp = a.src + ((size_t)b * a.C + c) * HW;
         const float* tp = a.tgt + ((size_t)b * a.C + c) * HW;
         float* vimg = a.vis + ((size_t)b * a.C + c) * HW;
+        for (int xt = 0; xt < a.ntile; ++xt) {
+        const int X0 = xt * 4 * a.GT;  // first source (= image column) of this x-tile
         __syncthreads();
         for (int t = tid; t < total_floats / 4; t += nthreads)
             reinterpret_cast<float4*>(sm)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
-        stage_row<PS>(a, sp, tp, dimg, mimg, i0, 0, true, sRs, sLs, PsW, PsC);
+        stage_row<PS>(a, sp, tp, dimg, mimg, i0, X0, 0, true, sRs, sLs, PsW, PsC);
         __syncthreads();
 
         for (int ii = 0; ii < rows_here; ++ii) {
             const int i = i0 + ii, buf = a.nbuf == 2 ? (ii & 1) : 0;
             if (a.nbuf == 2 && ii + 1 < rows_here)
-                stage_row<PS>(a, sp, tp, dimg, mimg, i + 1, buf ^ 1, false, sRs, sLs, PsW, PsC);
+                stage_row<PS>(a, sp, tp, dimg, mimg, i + 1, X0, buf ^ 1, false, sRs, sLs, PsW, PsC);
 
             // ---------------- taps of row i ----------------
             const int e0 = (i - T::P + T::YB) & 1;
@@ -400,7 +454,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) patch_loss_fold_v3_kernel(cons
             k += __shfl_xor_sync(0xffffffffu, b1 ? k0 : k1, 2);                                                         \
             k += __shfl_xor_sync(0xffffffffu, k, 1);                                                                    \
             const int t = (b2 ? 2 : 0) + (b1 ? 1 : 0);                                                                  \
-            const int j = 4 * gg + t;                                                                                   \
+            const int j = X0 + 4 * gg + t;                                                                              \
             if ((lane & 1) == 0 && j < W) {                                                                             \
                 const int cd = t == 0 ? c4.x : (t == 1 ? c4.y : (t == 2 ? c4.z : c4.w));                                \
                 const float g = (cd & 4) ? k : 0.f;                                                                     \
@@ -434,57 +488,32 @@ __global__ void __launch_bounds__(kMaxThreads, 1) patch_loss_fold_v3_kernel(cons
             // ---------------- Fold row y = i - p is complete: write it out ----------------
             {
                 const int y = i - T::P;
-                const int pidy = pid0, half = e0;  // ky = 0 is (r = 0, half e0)
-                const bool store = y >= 0;
+                const int half = e0;  // ky = 0 is (r = 0, half e0) of pair pid0
                 const bool shared_row = (i0 > 0 && y < i0 + T::P) || (i0 + rows_here < H && y > i0 + rows_here - 1 - T::P);
-                const float* vr = Vacc + ((size_t)(pidy % T::RING) * a.PV) * 2 + half;
-                float* vz = Vacc + ((size_t)(pidy % T::RING) * a.PV) * 2;
-                const int SW = 64 * a.n;
-                for (int x = tid; x < W; x += nthreads) {
-                    const int w0 = x / SW, xl = x - w0 * SW;
-                    const int li = w0 * RWd + xl + T::P;
-                    float v = 0.f;
-                    if (xl < T::P && w0 > 0) v += vr[2 * (li - RWd + SW)];           // overhang of the strip to the left
-                    v += vr[2 * li];
-                    if (xl >= SW - T::P && w0 + 1 < a.NW) v += vr[2 * (li + RWd - SW)];  // strip to the right
-                    if (store) {
-                        float* op = vimg + (size_t)y * W + x;
-                        if (shared_row) atomicAdd(op, v);
-                        else *op = v;
-                    }
-                    if (half == 1) {  // both rows of the pair are out: recycle the slot
-                        if (xl < T::P && w0 > 0) *reinterpret_cast<float2*>(vz + 2 * (li - RWd + SW)) = make_float2(0.f, 0.f);
-                        *reinterpret_cast<float2*>(vz + 2 * li) = make_float2(0.f, 0.f);
-                        if (xl >= SW - T::P && w0 + 1 < a.NW)
-                            *reinterpret_cast<float2*>(vz + 2 * (li + RWd - SW)) = make_float2(0.f, 0.f);
-                    }
-                }
+                float* vz = Vacc + ((size_t)(pid0 % T::RING) * a.PV) * 2;
+                // half == 1: both rows of the pair are out -> the slot is cleared for the pair that enters >= 3 rows later
+                const size_t sbo = (size_t)(y - (i0 - T::P)) * 2 * T::P, sbh = (size_t)a.sb_rows * 2 * T::P;
+                emit_row<PS>(a, vz, half, half == 1, SB + ((xt + 1) & 1) * sbh + sbo, SB + (xt & 1) * sbh + sbo,
+                             vimg + (size_t)max(y, 0) * W, shared_row, y >= 0, xt, X0, RWd);
             }
             if (a.nbuf == 1 && ii + 1 < rows_here) {
-                stage_row<PS>(a, sp, tp, dimg, mimg, i + 1, 0, false, sRs, sLs, PsW, PsC);
+                stage_row<PS>(a, sp, tp, dimg, mimg, i + 1, X0, 0, false, sRs, sLs, PsW, PsC);
                 __syncthreads();
             }
         }
         __syncthreads();
         // Fold rows still open at the end of the band: y in (i_last - p, i_last + p]
         const int i_last = i0 + rows_here - 1;
-        const int SW = 64 * a.n;
-        for (int t = tid; t < 2 * T::P * W; t += nthreads) {
-            const int yy = t / W, x = t - yy * W;
+        for (int yy = 0; yy < 2 * T::P; ++yy) {
             const int y = i_last - T::P + 1 + yy;
             if (y < 0 || y >= H) continue;
             const int pid = (y + T::YB) >> 1, half = (y + T::YB) & 1;
-            const float* vr = Vacc + ((size_t)(pid % T::RING) * a.PV) * 2 + half;
-            const int w0 = x / SW, xl = x - w0 * SW;
-            const int li = w0 * RWd + xl + T::P;
-            float v = 0.f;
-            if (xl < T::P && w0 > 0) v += vr[2 * (li - RWd + SW)];
-            v += vr[2 * li];
-            if (xl >= SW - T::P && w0 + 1 < a.NW) v += vr[2 * (li + RWd - SW)];
             const bool shared_row = (i0 > 0 && y < i0 + T::P) || (i_last + 1 < H && y > i_last - T::P);
-            if (shared_row) atomicAdd(vimg + (size_t)y * W + x, v);
-            else vimg[(size_t)y * W + x] = v;
+            const size_t sbo = (size_t)(y - (i0 - T::P)) * 2 * T::P, sbh = (size_t)a.sb_rows * 2 * T::P;
+            emit_row<PS>(a, Vacc + ((size_t)(pid % T::RING) * a.PV) * 2, half, false, SB + ((xt + 1) & 1) * sbh + sbo,
+                         SB + (xt & 1) * sbh + sbo, vimg + (size_t)y * W, shared_row, true, xt, X0, RWd);
         }
+        }  // x-tiles
     }
     const double bs = block_sum(tot, red);
     const double bc = block_sum(cnt, red);
@@ -507,23 +536,31 @@ static int launch(Args a, int B, int* nbands_out, cudaStream_t st) {
     auto round_pitch = [](int v) { v = (v + 1) & ~1; return (v & 3) == 2 ? v : v + 2; };  // even, half of it odd
     int best_n = 0;
     size_t smem = 0;
-    for (int n = 1; n <= 8 && best_n == 0; ++n) {
-        const int NW = (G + 16 * n - 1) / (16 * n);
-        if (NW > max_warps) continue;
-        a.n = n;
-        a.NW = NW;
-        a.GT = 16 * n * NW;
-        a.PR = round_pitch(T::OFF_R + 4 * G + T::NV);
-        a.PL = round_pitch(4 * a.GT + T::NV);
-        a.PV = round_pitch(NW * (64 * n + 2 * T::P));
-        for (int nbuf = 2; nbuf >= 1; --nbuf) {
-            const size_t fl = (size_t)2 * nbuf * T::NP * a.PR + (size_t)2 * T::RING * a.PL + (size_t)2 * T::RING * a.PV +
-                              (size_t)2 * nbuf * 4 * a.GT;
-            if (fl * sizeof(float) <= 232448 - 1024) {
-                a.nbuf = nbuf;
-                smem = ((fl + 3) & ~(size_t)3) * sizeof(float);
-                best_n = n;
-                break;
+    // geometry: as few x-tiles as possible, then as few groups per walker as possible, double-buffered if it fits.
+    // The band size (hence the side buffer) is fixed afterwards; 2p * (H + 2p) floats bound it here.
+    for (int ntile = 1; ntile <= 4 && best_n == 0; ++ntile) {
+        const int Gt = (G + ntile - 1) / ntile;
+        for (int n = 1; n <= 8 && best_n == 0; ++n) {
+            const int NW = (Gt + 16 * n - 1) / (16 * n);
+            if (NW > max_warps) continue;
+            a.n = n;
+            a.NW = NW;
+            a.GT = 16 * n * NW;
+            a.ntile = (G + a.GT - 1) / a.GT;
+            a.PR = round_pitch(T::OFF_R + 4 * G + T::NV);
+            a.PL = round_pitch(4 * a.GT + T::NV);
+            a.PV = round_pitch(NW * (64 * n + 2 * T::P));
+            const size_t sb = a.ntile > 1 ? (size_t)4 * T::P * (H + 2 * T::P) : 0;
+            for (int nbuf = 2; nbuf >= 1; --nbuf) {
+                const size_t fl = (size_t)2 * nbuf * T::NP * a.PR + (size_t)2 * T::RING * a.PL +
+                                  (size_t)2 * T::RING * a.PV + (size_t)2 * nbuf * 4 * a.GT;
+                const size_t sb_cap = sb < 16384 ? sb : 16384;  // the side buffer only needs band_rows + 2p rows
+                if ((fl + sb_cap) * sizeof(float) <= 232448 - 1024) {
+                    a.nbuf = nbuf;
+                    smem = ((fl + 3) & ~(size_t)3) * sizeof(float);
+                    best_n = n;
+                    break;
+                }
             }
         }
     }
@@ -547,6 +584,11 @@ static int launch(Args a, int B, int* nbands_out, cudaStream_t st) {
         if (rows <= 4) break;
     }
     a.band_rows = (H + best_nb - 1) / best_nb;
+    a.sb_rows = a.band_rows + 2 * T::P;
+    if (a.ntile > 1) {
+        smem += (size_t)2 * a.sb_rows * 2 * T::P * sizeof(float);
+        if (smem > 232448 - 1024) return AZ_ERR_BAD_ARG;
+    }
     const int nbands = (H + a.band_rows - 1) / a.band_rows;
     if (nbands > 65535) return AZ_ERR_BAD_ARG;
     *nbands_out = nbands;

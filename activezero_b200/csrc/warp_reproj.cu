@@ -684,9 +684,12 @@ extern "C" int az_reproj_loss_fwd(const float* tgt, const float* src, const floa
     const int p = (int)(ps - 1) / 2;
     const size_t Wp = (size_t)W + 2 * (p + 1);
     const size_t smem = 2 * (size_t)ps * Wp * sizeof(float);
-    if (smem > 220 * 1024) return AZ_ERR_BAD_ARG;
     double* partial = (double*)workspace;
     int rc;
+    // round 1's kernels stage full rows of width W + ps + 1: beyond ~2600 columns at ps = 11 only the x-tiled round-2
+    // kernel (loss + Fold image) can run
+    const bool r1_fits = smem <= 220 * 1024;
+    if (!r1_fits && !(warped != nullptr && ps != 1)) return AZ_ERR_BAD_ARG;
     if (warped != nullptr && ps != 1) {
         // get_reproj_error_patch: loss + Fold image in one pass (patch_loss_fold.cu) when the shape fits its
         // shared-memory plan, else the stand-alone loss kernel followed by the stand-alone Fold
@@ -697,7 +700,7 @@ extern "C" int az_reproj_loss_fwd(const float* tgt, const float* src, const floa
         if (H <= (1 << 24) && tuning("AZ_PATCH_IMPL", 1) == 1)
             rc = plf3_dispatch(tgt, src, disp, sign, mask, lin_x, lin_y, (int)ps, warped, gpre, partial, (int)B, (int)C,
                                (int)H, (int)W, &nbands, st);
-        if (rc == AZ_ERR_BAD_ARG && H <= (1 << 24))
+        if (rc == AZ_ERR_BAD_ARG && H <= (1 << 24) && r1_fits)
             rc = plf_dispatch(tgt, src, disp, sign, mask, lin_x, lin_y, (int)ps, warped, gpre, partial, (int)B, (int)C,
                               (int)H, (int)W, &nbands, st);
         if (rc == 0) {
@@ -705,7 +708,7 @@ extern "C" int az_reproj_loss_fwd(const float* tgt, const float* src, const floa
             AZ_LAUNCH_CHECK();
             return 0;
         }
-        if (rc != AZ_ERR_BAD_ARG) return rc;
+        if (rc != AZ_ERR_BAD_ARG || !r1_fits) return rc;
         rc = az_reproj_loss_fwd(tgt, src, disp, sign, mask, lin_x, lin_y, ps, nullptr, gpre, loss_out, stats, workspace,
                                 B, C, H, W, stream);
         if (rc != 0) return rc;

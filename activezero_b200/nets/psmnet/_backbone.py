@@ -138,6 +138,11 @@ class PSMNetBase(nn.Module):
         # format, in which cuDNN runs the 3-D aggregation below without layout passes
         # (2-2.6x faster on B200, benchmarks/agg_layout_probe.py).  Set it with use_channels_last_3d().
         self.volume_channels_last = False
+        # True (inference only): dres0's first Conv3d + BatchNorm + ReLU run as ONE tensor-core kernel that gathers the
+        # concat volume's values straight from the two feature maps (implicit clause): the
+        # [B,64,D/4,H/4,W/4] volume is never written nor re-read.  TF32 operands like cuDNN's default conv path.
+        self.fuse_volume_conv = False
+        self._vc_cache = None
         self.feature_extraction = feature_extraction
         self.dres0 = nn.Sequential(convbn_3d(64, 32, 3, 1, 1), nn.ReLU(inplace=True),
                                    convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True))
@@ -175,9 +180,22 @@ class PSMNetBase(nn.Module):
                 m.weight.data = m.weight.data.contiguous(memory_format=fmt)
         return self
 
-    def _aggregate(self, cost):
-        """psmnet.py:167-181: dres0..4 and the three residual classification heads."""
-        cost0 = self.dres0(cost)
+    def _first_conv_implicit(self, ref_feat, tgt_feat):
+        """dres0[0] (Conv3d 64->32 + BatchNorm3d, eval statistics) + dres0[1] (ReLU) on the IMPLICIT volume."""
+        from ... import ops
+
+        conv, bn = self.dres0[0][0], self.dres0[0][1]
+        key = (conv.weight.data_ptr(), conv.weight._version, str(conv.weight.device))
+        if self._vc_cache is None or self._vc_cache[0] != key:
+            self._vc_cache = (key, ops.pack_volume_conv_weight(conv.weight))
+        scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+        shift = bn.bias.detach() - bn.running_mean * scale
+        return ops.volume_conv0(ref_feat, tgt_feat, self._vc_cache[1], self.maxdisp // 4, scale, shift, relu=True)
+
+    def _aggregate(self, cost, first=None):
+        """psmnet.py:167-181: dres0..4 and the three residual classification heads.  ``first`` = output of
+        dres0[0:2] when it was computed on the implicit volume."""
+        cost0 = self.dres0(cost) if first is None else self.dres0[3](self.dres0[2](first))
         cost0 = self.dres1(cost0) + cost0
         out1, pre1, post1 = self.dres2(cost0, None, None)
         out1 = out1 + cost0
@@ -205,6 +223,12 @@ class PSMNetBase(nn.Module):
         from ... import ops
 
         H, W = ref_feat.shape[-2:]
+        if self.fuse_volume_conv and not self.training and not torch.is_grad_enabled() and ref_feat.shape[1] == 32:
+            first = self._first_conv_implicit(ref_feat, tgt_feat)
+            if self.volume_channels_last:
+                first = first.contiguous(memory_format=torch.channels_last_3d)
+            _, _, cost3 = self._aggregate(None, first)
+            return self._disparity_head(cost3, H, W)
         if self.volume_channels_last:
             cost = ops.build_concat_volume(ref_feat, tgt_feat, self.maxdisp // 4, channels_last=True)
         else:

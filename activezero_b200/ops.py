@@ -133,6 +133,44 @@ def build_concat_volume(ref_feat, tgt_feat, num_disp: int, channels_last: bool =
 
 
 # ----------------------------------------------------------------------------
+# §8f rank 2: dres0's first convolution with the concat volume left implicit (tcgen05 TF32 implicit GEMM)
+# ----------------------------------------------------------------------------
+def pack_volume_conv_weight(weight: torch.Tensor) -> torch.Tensor:
+    """Conv3d weight [32,64,3,3,3] (dres0[0][0].weight, psmnet.py:85-90) -> the per-tap core-matrix order of the
+    tensor-core kernel, rounded to TF32; do this once per weight tensor."""
+    w = _cuda_f32(weight.detach(), "weight")
+    if tuple(w.shape) != (32, 64, 3, 3, 3):
+        raise ValueError(f"volume conv: expected a [32,64,3,3,3] Conv3d weight, got {tuple(w.shape)}")
+    packed = torch.empty((27, 32 * 64), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.call("az_volume_conv0_pack", _ptr(w), _ptr(packed), _stream())
+    return packed
+
+
+def volume_conv0(ref_feat, tgt_feat, wpacked, num_disp: int, scale=None, shift=None, relu: bool = False):
+    """conv3d(concat_volume(ref, tgt, num_disp), weight, padding=1) without the volume (forward only; TF32 operands,
+    fp32 accumulation): [B,32,H,W] x2 -> [B,32,num_disp,H,W].  ``scale``/``shift`` [32] fold an eval-mode BatchNorm."""
+    L, R = check_feature_pair(ref_feat.detach(), tgt_feat.detach(), "volume conv")
+    B, C, H, W = L.shape
+    if C != 32:
+        raise ValueError("volume conv: PSMNet's 32 feature channels expected")
+    wp = _cuda_f32(wpacked, "wpacked")
+    if wp.numel() != 27 * 32 * 64 or wp.device != L.device:
+        raise ValueError("volume conv: wpacked must come from pack_volume_conv_weight on the features' device")
+    if (scale is None) != (shift is None):
+        raise ValueError("volume conv: scale and shift go together")
+    sc = _cuda_f32(scale.detach().reshape(-1), "scale") if scale is not None else None
+    sh = _cuda_f32(shift.detach().reshape(-1), "shift") if shift is not None else None
+    if sc is not None and (sc.numel() != 32 or sh.numel() != 32):
+        raise ValueError("volume conv: scale / shift must hold 32 values")
+    out = torch.empty((B, 32, int(num_disp), H, W), dtype=torch.float32, device=L.device)
+    with torch.cuda.device(L.device):
+        _lib.call("az_volume_conv0_fwd", _ptr(L), _ptr(R), _ptr(wp), _ptr(sc), _ptr(sh), _ptr(out), B, C, H, W, int(num_disp),
+                  1 if relu else 0, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------
 # a3 group-wise correlation volume (no reference counterpart)
 # ----------------------------------------------------------------------------
 class GwcVolumeFn(torch.autograd.Function):

@@ -316,21 +316,47 @@ def run_b200(args, rank, world, local_rank):
         for _ in range(args.warmup):
             out = step(L, R, cost, pat_L, pat_R, mask)
         del out
-        # ---- device-resident timing (value) + per-kernel events for the roofline ----
+        # ---- per-kernel CUDA events for the roofline: K eager steps, the three calls bracketed by events ----
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for k in range(args.steps):
+            out = step(L, R, cost, pat_L, pat_R, mask, evs[k])
+        e1.record()
+        barrier()
+        ms_eager = e0.elapsed_time(e1)
+        del out
+        # ---- device-resident timing (value): the step captured ONCE in a CUDA graph (the calls only enqueue on the
+        # caller's stream: no allocation, no sync, no host readback), then exactly K replays between the barriers.
+        # One graph launch per step keeps eight ranks' Python launch paths (4 host CPUs each) off the critical path;
+        # the eager figure above is reported next to it.
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step(L, R, cost, pat_L, pat_R, mask)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
         launches0 = _lib.kernel_launches
+        with torch.cuda.graph(graph):
+            gout = step(L, R, cost, pat_L, pat_R, mask)
+        launches_per_step = _lib.kernel_launches - launches0
+        for _ in range(2):
+            graph.replay()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         clocks.start()
         start.record()
         for k in range(args.steps):
-            out = step(L, R, cost, pat_L, pat_R, mask, evs[k])
+            graph.replay()
         stop.record()
         barrier()
         clocks.pause()
-        launches = _lib.kernel_launches - launches0
+        launches = launches_per_step * args.steps
         ms_total = start.elapsed_time(stop)
-        del out
+        loss_graph = float(gout[2])
+        del gout, graph
 
         # ---- end to end: pinned host -> device, compute, results back, every step ----
         e2e_steps = max(1, min(args.steps, 10))
@@ -511,8 +537,8 @@ def run_b200(args, rank, world, local_rank):
             stock = time_stock_torch_gpu(L[:STOCK_B], R[:STOCK_B], cost[:STOCK_B], pat_L[:STOCK_B], pat_R[:STOCK_B],
                                          mask[:STOCK_B])
 
-    ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train, ms_h2d, ms_fused_k = dist_util.max_over_ranks(
-        [ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train, ms_h2d, ms_fused_k], dev)
+    ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train, ms_h2d, ms_fused_k, ms_eager = dist_util.max_over_ranks(
+        [ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train, ms_h2d, ms_fused_k, ms_eager], dev)
 
     if rank == 0:
         per_kernel = {}
@@ -550,6 +576,8 @@ def run_b200(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "launch": "one CUDA-graph replay per step (captured once; 3 C-ABI calls, %d kernels + 1 memset)" % launches_per_step,
+            "ms_per_step_eager": ms_eager / args.steps, "value_eager": world * B * args.steps / (ms_eager * 1e-3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": CONFIG,
             "clocks": clk,
@@ -581,7 +609,7 @@ def run_b200(args, rank, world, local_rank):
                     "ms": ms_fused_k, "bound": "mufu", "ex2_per_launch": FUSED_EX2, "achieved": FUSED_EX2 / (ms_fused_k * 1e-3),
                     "peak": NUM_SMS * 16 * sm_hz, "unit": "ex2/s", "frac": FUSED_EX2 / (ms_fused_k * 1e-3) / (NUM_SMS * 16 * sm_hz),
                     "peak_source": "148 SMs x 16 MUFU lanes per clock x sampled SM clock"}},
-            "loss_check": loss_val,
+            "loss_check": loss_val, "loss_check_graph": loss_graph,
         }
         if not args.no_train_variant:
             pairs_s = world * TRAIN_B * TRAIN_STEPS / (ms_train * 1e-3)

@@ -44,7 +44,7 @@ class env:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
-    ap.add_argument("--only", default="sa,concat,gwc,usa,patch")
+    ap.add_argument("--only", default="sa,concat,gwc,usa,patch,vconv")
     args = ap.parse_args()
     only = set(args.only.split(","))
     pk = peak()
@@ -118,6 +118,28 @@ def main():
                     add("gwc_volume_bwd", f"AZ_GWC_BWD={v}",
                         time_ms(lambda: _lib.call("az_gwc_volume_bwd", _ptr(g), _ptr(L), _ptr(R), _ptr(gL), _ptr(gR), B, C, Hq, Wq,
                                                   Dq, G, _stream()), flush=True), nbb)
+        if "vconv" in only:
+            import torch.nn.functional as F
+
+            Bc = 2
+            L, R = torch.randn(Bc, C, Hq, Wq, device=DEV), torch.randn(Bc, C, Hq, Wq, device=DEV)
+            w = torch.randn(32, 64, 3, 3, 3, device=DEV) * 0.05
+            wp = ops.pack_volume_conv_weight(w)
+            flops = 2.0 * Bc * Dq * Hq * Wq * 32 * 64 * 27
+            nb = 4 * (2 * C * Hq * Wq + 32 * Dq * Hq * Wq) * Bc  # features in, conv output out (no volume)
+
+            def stock():
+                return F.conv3d(ops.build_concat_volume(L, R, Dq), w, padding=1)
+
+            wcl = w.contiguous(memory_format=torch.channels_last_3d)
+
+            def stock_cl():
+                return F.conv3d(ops.build_concat_volume(L, R, Dq, channels_last=True), wcl, padding=1)
+
+            for name, fn in (("implicit volume, tcgen05 TF32 (this repo)", lambda: ops.volume_conv0(L, R, wp, Dq)),
+                             ("az volume + cuDNN conv3d NCDHW (TF32)", stock), ("az volume (channels_last_3d) + cuDNN conv3d", stock_cl)):
+                ms = time_ms(fn, flush=True)
+                add("dres0_first_conv", name, ms, nb, {"TFLOPs": round(flops / ms / 1e9, 1), "pairs": Bc})
         if "patch" in only:
             gen = torch.Generator().manual_seed(5)
             pL = (torch.rand(B, 1, H, W, generator=gen) > 0.5).float().to(DEV)

@@ -52,6 +52,17 @@ int az_concat_volume_fwd_ndhwc(const float* L, const float* R, float* vol,
 int az_concat_volume_bwd_ndhwc(const float* gvol, float* gL, float* gR,
                                int64_t B, int64_t C, int64_t H, int64_t W, int64_t Dq, void* stream);
 
+/* ---- SURVEY.md §8f rank 2, implicit clause: the first 3-D convolution of the aggregation with the volume left
+ *      implicit -- nets/psmnet/psmnet.py:151-168 (volume + dres0[0] = Conv3d(64,32,3,1,1,bias=False)), psmnet_submodule.py:44-56.
+ * out[b,co,d,y,x] = sum_{ci,kd,ky,kx} weight[co,ci,kd,ky,kx] * vol[b,ci,d+kd-1,y+ky-1,x+kx-1] (zero padding) with vol
+ * the concat volume of az_concat_volume_fwd, never materialised: tcgen05 TF32 implicit GEMM, fp32 accumulation in
+ * tensor memory.  L,R: [B,32,H,W]; out: [B,32,Dq,H,W]; wpacked: 27*32*64 floats produced ONCE per weight tensor by
+ * az_volume_conv0_pack from the Conv3d weight [32,64,3,3,3]; scale/shift: float[32] or both NULL (an eval-mode
+ * BatchNorm folded into the epilogue: out*scale+shift), relu != 0 applies max(.,0) last. */
+int az_volume_conv0_pack(const float* weight, float* wpacked, void* stream);
+int az_volume_conv0_fwd(const float* L, const float* R, const float* wpacked, const float* scale, const float* shift,
+                        float* out, int64_t B, int64_t C, int64_t H, int64_t W, int64_t Dq, int relu, void* stream);
+
 /* ---- a3: group-wise correlation volume -- NOT IN THE REFERENCE (parity unpinned) ----
  * vol[b,g,i,y,x] = (1/(C/G)) * sum_{c in group g} L[b,c,y,x]*R[b,c,y,x-i]  (x >= i, else 0); vol: [B,G,Dq,H,W]. */
 int az_gwc_volume_fwd(const float* L, const float* R, float* vol,

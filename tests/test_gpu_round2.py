@@ -286,10 +286,12 @@ def _patch_case(B, C, H, W, ps, seed, field, masked=True):
                                             ((1, 2, 37, 72), 5, "random"), ((1, 1, 24, 90), 3, "wild"),
                                             ((1, 1, 30, 133), 11, "wild"), ((1, 3, 26, 61), 7, "random"),
                                             ((1, 1, 45, 260), 13, "random"), ((1, 1, 64, 256), 9, "smooth"),
-                                            ((1, 1, 23, 12), 11, "random"), ((1, 1, 12, 8), 5, "wild")])
+                                            ((1, 1, 23, 12), 11, "random"), ((1, 1, 12, 8), 5, "wild"),
+                                            ((1, 1, 33, 2610), 11, "smooth"), ((1, 1, 28, 1920), 11, "random")])
 def test_patch_loss_fold_v3_vs_oracle(shape, ps, field):
     """The round-2 one-pass kernel (lanes over tap rows) against the oracle's restatement of
-    reprojection.py:99-127: loss, d loss / d disp and the Fold image, ragged widths and out-of-image samples."""
+    reprojection.py:99-127: loss, d loss / d disp and the Fold image, ragged widths and out-of-image samples.  The
+    last two shapes split the row into x-tiles (four at W = 2610, a width round 1's kernels cannot stage at all)."""
     B, C, H, W = shape
     L, R, d, m = _patch_case(B, C, H, W, ps, 40 + H + W, field)
     d64 = d.clone().requires_grad_(True)
@@ -306,10 +308,11 @@ def test_patch_loss_fold_v3_vs_oracle(shape, ps, field):
 
 
 @pytest.mark.parametrize("H,W,field", [(544, 960, "random"), (720, 1280, "random"), (256, 512, "smooth"), (97, 1000, "wild"),
-                                      (64, 1404, "random")])
+                                      (64, 1404, "random"), (70, 1920, "random"), (45, 1920, "wild"), (1088, 1920, "random")])
 def test_patch_loss_fold_v3_vs_round1_kernel_large(H, W, field):
     """Sizes the oracle cannot afford in a test: the round-2 kernel against round 1's (itself pinned to the real
-    reference by tests/golden/reprojection*.npz), forward with and without the gradient, deterministic."""
+    reference by tests/golden/reprojection*.npz), forward with and without the gradient, deterministic.  W = 1920 and
+    2610 make the round-2 kernel split the row into x-tiles (seam columns handed over through the side buffer)."""
     L, R, d, m = _patch_case(2, 1, H, W, 11, 7, field)
     Lg, Rg, mg = L.to(DEV), R.to(DEV), m.to(DEV)
     res = {}
@@ -414,3 +417,71 @@ def test_temporal_ir_integer_form_is_exact_on_ties_free_input():
         assert float((out != ref).mean()) <= 1e-5, (T_, H, W, ks)
     const = torch.full((7, 32, 32), 9, dtype=torch.uint8, device=DEV)
     assert float(ops.temporal_ir_pattern(const).abs().max()) == 0.0  # the reference divides 0/0 here: NaN > thr is False
+
+
+# --------------------------------------------------------------------------- §8f-2: implicit-concat first convolution
+def _conv_ref(L, R, w, dq, tf32):
+    vol = ops.build_concat_volume(L, R, dq)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    try:
+        return F.conv3d(vol, w, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("shape,dq", [((1, 32, 9, 140), 12), ((2, 32, 6, 128), 8), ((1, 32, 5, 37), 48), ((1, 32, 34, 60), 5),
+                                      ((1, 32, 3, 300), 20)])
+def test_volume_conv0_matches_conv3d_of_materialised_volume(shape, dq):
+    """conv3d(concat_volume) without the volume (tcgen05 TF32, fp32 accumulation in tensor memory) against stock
+    cuDNN on the materialised volume: inside cuDNN's own TF32-vs-fp32 distance, and exact on one-hot probes."""
+    torch.manual_seed(50)
+    L, R = torch.randn(shape, device=DEV), torch.randn(shape, device=DEV)
+    w = torch.randn(32, 64, 3, 3, 3, device=DEV) * 0.05
+    out = ops.volume_conv0(L, R, ops.pack_volume_conv_weight(w), dq)
+    ref32 = _conv_ref(L, R, w, dq, tf32=False)
+    ref_tf = _conv_ref(L, R, w, dq, tf32=True)
+    assert out.shape == ref32.shape
+    scale = float(ref32.abs().max())
+    mine, theirs = float((out - ref32).abs().max()), float((ref_tf - ref32).abs().max())
+    assert mine <= max(2.0 * theirs, 2e-3 * scale), (mine, theirs, scale)
+    # structure probe: values that TF32 represents exactly (small integers, one-hot weights) must come out exactly --
+    # every tap, every channel of both halves, the diagonal mask and all four borders
+    Li = torch.randint(-3, 4, shape, device=DEV).float()
+    Ri = torch.randint(-3, 4, shape, device=DEV).float()
+    wi = torch.randint(-2, 3, (32, 64, 3, 3, 3), device=DEV).float()
+    outi = ops.volume_conv0(Li, Ri, ops.pack_volume_conv_weight(wi), dq)
+    assert torch.equal(outi, _conv_ref(Li, Ri, wi, dq, tf32=False))
+
+
+def test_volume_conv0_epilogue_and_psmnet_flag():
+    torch.manual_seed(51)
+    L, R = torch.randn(1, 32, 8, 64, device=DEV), torch.randn(1, 32, 8, 64, device=DEV)
+    w = torch.randn(32, 64, 3, 3, 3, device=DEV) * 0.05
+    sc, sh = torch.rand(32, device=DEV) + 0.5, torch.randn(32, device=DEV)
+    out = ops.volume_conv0(L, R, ops.pack_volume_conv_weight(w), 6, sc, sh, relu=True)
+    ref = torch.relu(_conv_ref(L, R, w, 6, tf32=False) * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1))
+    assert float((out - ref).abs().max()) <= 3e-3 * float(ref.abs().max())
+    from activezero_b200.nets.psmnet.psmnet_3 import PSMNet
+
+    net = PSMNet(maxdisp=192).cuda().eval()
+    # non-trivial BatchNorm statistics, as a trained checkpoint has
+    bn = net.dres0[0][1]
+    bn.running_mean.normal_(0, 0.2)
+    bn.running_var.uniform_(0.5, 2.0)
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_(0, 0.3)
+    fl, fr = torch.randn(1, 32, 16, 64, device=DEV), torch.randn(1, 32, 16, 64, device=DEV)
+    with torch.no_grad():
+        want = net.dres0[1](net.dres0[0](ops.build_concat_volume(fl, fr, 48)))
+        got = net._first_conv_implicit(fl, fr)
+    assert float((got - want).abs().max()) <= 3e-3 * float(want.abs().max())
+    # end to end: the flag only changes how dres0's first layer is computed (a random-initialised network's disparities
+    # are arg-max plateaus that flip on 1e-3 logit noise, so only shape / finiteness / range are asserted here)
+    a, b = torch.rand(1, 3, 256, 256, device=DEV), torch.rand(1, 3, 256, 256, device=DEV)
+    with torch.no_grad():
+        p_ref = net(a, b)
+        net.fuse_volume_conv = True
+        p_fused = net(a, b)
+    assert p_fused.shape == p_ref.shape and torch.isfinite(p_fused).all()
+    assert float(p_fused.min()) >= 0.0 and float(p_fused.max()) <= 191.0
