@@ -67,7 +67,19 @@ __global__ void __launch_bounds__(256) tir_slope_kernel(const uint8_t* __restric
         mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
+    // one atomic pair per CTA (per-warp atomics on the 2 words of an image serialise in L2: 130 k of them at 544x960)
+    __shared__ int smn[8], smx[8];
     if ((threadIdx.x & 31) == 0) {
+        smn[threadIdx.x >> 5] = mn;
+        smx[threadIdx.x >> 5] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            mn = min(mn, smn[k]);
+            mx = max(mx, smx[k]);
+        }
         atomicMin(&minmax[2 * b], mn);
         atomicMax(&minmax[2 * b + 1], mx);
     }

@@ -10,23 +10,28 @@
 // This is the one place on the hot path that is a dense contraction, so it runs on the 5th-generation tensor
 // cores: an implicit GEMM with M = 128 consecutive x positions of one (b, d, y) row, N = 32 output channels and
 // K = 27 taps x 64 channels, TF32 operands, fp32 accumulation in TENSOR MEMORY.
-//   * the A operand of a tap (128 positions x 64 channels) is GATHERED straight from the two feature maps (left
-//     half: the row itself, masked below the diagonal x' < d'; right half: the row shifted by d') into shared
-//     memory in the canonical K-major core-matrix layout (8 rows x 16 bytes, no swizzle), rounded to TF32
-//     (cvt.rna); the 401 MB-per-pair volume and cuDNN's re-read of it disappear;
+//   * the A operand is GATHERED straight from the two feature maps (left half: the row itself, masked below the
+//     diagonal x' < d'; right half: the row shifted by d') into shared memory in the canonical K-major core-matrix
+//     layout (8 rows x 16 bytes, no swizzle), rounded to TF32 (cvt.rna) -- one 130-row slab per (kd, ky), which the
+//     three kx taps read through descriptors whose start address differs by one 16-byte row; the 401 MB-per-pair
+//     volume and cuDNN's re-read of it disappear;
 //   * the B operand of a tap (32 x 64 weights) is pre-packed on the device once per weight tensor in the same
 //     core-matrix order and copied linearly;
-//   * one elected thread issues eight tcgen05.mma.cta_group::1.kind::tf32 (M128 N32 K8) per tap and commits them
-//     to an mbarrier; two shared-memory stages, so the gather of tap t+1 overlaps the MMAs of tap t;
+//   * one elected thread issues 3 x 8 tcgen05.mma.cta_group::1.kind::tf32 (M128 N32 K8) per slab and commits them
+//     to an mbarrier; two shared-memory stages, so the gather of slab t+1 overlaps the MMAs of slab t;
 //   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> optional per-channel scale / shift (an eval-mode
 //     BatchNorm folded in) and ReLU -> coalesced stores in NCDHW.
-// grid = (ceil(W/128), H, Dq*B), 256 threads, 80 KB dynamic shared memory, 32 TMEM columns.
+// grid = (ceil(W/128), H, Dq*B), 256 threads, 116 KB dynamic shared memory, 32 TMEM columns.
 #include "common.cuh"
 
 namespace az {
 
 constexpr int kVcThreads = 256, kVcM = 128, kVcN = 32, kVcC = 32, kVcK = 64;
-constexpr int kVcABytes = kVcM * kVcK * 4, kVcBBytes = kVcN * kVcK * 4, kVcStage = kVcABytes + kVcBBytes;
+constexpr int kVcSlabGroups = 17;                        // 8-row groups of a slab: rows u = 0..135, 130 of them used
+constexpr int kVcChunk = kVcSlabGroups * 8 * 16;         // bytes of one 4-channel chunk of a slab (rows at 16 B)
+constexpr int kVcABytes = (kVcK / 4) * kVcChunk;         // 16 chunks = 64 channels
+constexpr int kVcBBytes = 3 * kVcN * kVcK * 4;           // the three kx taps of a (kd, ky)
+constexpr int kVcStage = kVcABytes + kVcBBytes;
 
 __device__ __forceinline__ uint64_t vc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     // cute::UMMA::SmemDescriptor: start address [0,14), leading byte offset [16,30), stride byte offset [32,46)
@@ -74,35 +79,46 @@ __global__ void __launch_bounds__(kVcThreads) volume_conv0_kernel(const float* _
     const uint32_t tmem = tmem_base_s;
 
     const int r = lane & 7, e = lane >> 3;  // row within a core matrix, element within its 16-byte row
-    int it = 0;                             // taps issued so far
-    for (int tap = 0; tap < 27; ++tap) {
-        const int kd = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
+    int it = 0;                             // (kd, ky) slabs issued so far
+    for (int kdy = 0; kdy < 9; ++kdy) {
+        const int kd = kdy / 3, ky = kdy % 3;
         const int dp = d + kd - 1, yp = y + ky - 1;
-        if (dp < 0 || dp >= Dq || yp < 0 || yp >= H) continue;  // the whole tap reads the volume's zero padding
+        if (dp < 0 || dp >= Dq || yp < 0 || yp >= H) continue;  // these three taps read the volume's zero padding
         const int stage = it & 1;
         if (it >= 2) mbar_wait(&bars[stage], (uint32_t)(((it >> 1) - 1) & 1));  // the MMAs that read this stage are done
         unsigned char* As = vsm + (size_t)stage * kVcStage;
         unsigned char* Bs = As + kVcABytes;
-        // ---- B: 8 KB of pre-packed weights, linear copy
+        // ---- B: the three kx taps of (kd, ky) are consecutive in wpacked: 24 KB, linear copy
         {
-            const float4* src = reinterpret_cast<const float4*>(wpacked + (size_t)tap * kVcN * kVcK);
+            const float4* src = reinterpret_cast<const float4*>(wpacked + (size_t)(3 * kdy) * kVcN * kVcK);
             float4* dst = reinterpret_cast<float4*>(Bs);
-            dst[tid] = __ldg(src + tid);
-            dst[tid + kVcThreads] = __ldg(src + tid + kVcThreads);
-        }
-        // ---- A: warp w gathers the channel quads kq = 2w, 2w+1 (k = 4 kq + e) for all 16 row groups
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int kq = 2 * warp + h, ci = 4 * kq + e;
-            const bool right = ci >= kVcC;
-            const float* plane = (right ? R : L) + ((size_t)b * kVcC + (right ? ci - kVcC : ci)) * HW + (size_t)yp * W;
-            unsigned char* dstk = As + (size_t)(kq >> 1) * 4096 + (size_t)(kq & 1) * 2048 + (size_t)r * 16 + (size_t)e * 4;
-#pragma unroll 4
-            for (int mg = 0; mg < 16; ++mg) {
-                const int xp = x0 + 8 * mg + r + kx - 1;
-                float v = 0.f;
-                if (xp >= dp && xp < W && xp >= 0) v = __ldg(plane + (right ? xp - dp : xp));
-                *reinterpret_cast<float*>(dstk + (size_t)mg * 128) = to_tf32(v);
+            for (int k = 0; k < 6; ++k) dst[tid + k * kVcThreads] = __ldg(src + tid + k * kVcThreads);
+        }
+        // ---- A: ONE slab per (kd, ky) serves the three kx taps.  In the no-swizzle K-major layout a 4-channel chunk
+        //      is linear in the row: byte 16 m + 4 e (8 rows x 16 B per core matrix, SBO = 128 B), so tap kx is the same
+        //      slab read from a start address kx * 16 bytes further.  Slab row u holds volume column x' = x0 + u - 1.
+        //      Warp w gathers the chunks kq = 2w, 2w+1 (k = 4 kq + e) for the 17 row groups; all of a thread's loads
+        //      are issued before the first one is consumed (the gather is latency-bound).
+        {
+            float v[2][kVcSlabGroups];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ci = 4 * (2 * warp + h) + e;
+                const bool right = ci >= kVcC;
+                const float* plane = (right ? R : L) + ((size_t)b * kVcC + (right ? ci - kVcC : ci)) * HW + (size_t)yp * W;
+                const int sh = right ? dp : 0;
+#pragma unroll
+                for (int ug = 0; ug < kVcSlabGroups; ++ug) {
+                    const int xp = x0 + 8 * ug + r - 1;
+                    v[h][ug] = (xp >= dp && xp < W && xp >= 0) ? __ldg(plane + xp - sh) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                unsigned char* dstk = As + (size_t)(2 * warp + h) * kVcChunk + (size_t)r * 16 + (size_t)e * 4;
+#pragma unroll
+                for (int ug = 0; ug < kVcSlabGroups; ++ug) *reinterpret_cast<float*>(dstk + (size_t)ug * 128) = to_tf32(v[h][ug]);
             }
         }
         fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
@@ -111,15 +127,19 @@ __global__ void __launch_bounds__(kVcThreads) volume_conv0_kernel(const float* _
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a0 = sbase + (uint32_t)stage * kVcStage, b0 = a0 + kVcABytes;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint64_t da = vc_smem_desc(a0 + j * 4096, 2048, 128);
-                const uint64_t db = vc_smem_desc(b0 + j * 1024, 512, 128);
-                const uint32_t acc = (it > 0 || j > 0) ? 1u : 0u;
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
-                    ::"r"(tmem), "l"(da), "l"(db), "r"(kVcIdesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0)
-                    : "memory");
+            for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    // K8 slice j = chunks 2j and 2j+1 (LBO = chunk stride), rows linear at 16 B (SBO = 128 B per 8 rows)
+                    const uint64_t da = vc_smem_desc(a0 + (uint32_t)(2 * j) * kVcChunk + (uint32_t)kx * 16, kVcChunk, 128);
+                    const uint64_t db = vc_smem_desc(b0 + (uint32_t)kx * (kVcN * kVcK * 4) + j * 1024, 512, 128);
+                    const uint32_t acc = (it > 0 || kx > 0 || j > 0) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+                        ::"r"(tmem), "l"(da), "l"(db), "r"(kVcIdesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0)
+                        : "memory");
+                }
             }
             // completion of everything issued so far -> this stage's barrier (implies fence::before_thread_sync)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[stage]))

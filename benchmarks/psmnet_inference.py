@@ -79,6 +79,17 @@ def main():
         net.fuse_upsample = False
         res["az_ops_ndhwc_volume_ms"] = timed(lambda: net(x, y), args.iters)
         net.use_channels_last_3d(False)
+        # SURVEY.md §8f rank 2, implicit clause: dres0's first conv + BN + ReLU as the tcgen05 kernel on the implicit
+        # volume (the volume is never written); NCDHW aggregation, with and without the fused upsample
+        net.fuse_volume_conv = True
+        res["az_ops_implicit_volume_conv_ms"] = timed(lambda: net(x, y), args.iters)
+        net.fuse_upsample = True
+        res["az_ops_implicit_volume_conv_fused_upsample_ms"] = timed(lambda: net(x, y), args.iters)
+        net.use_channels_last_3d(True)
+        res["az_ops_implicit_volume_conv_fused_upsample_ndhwc_ms"] = timed(lambda: net(x, y), args.iters)
+        net.use_channels_last_3d(False)
+        net.fuse_upsample = False
+        net.fuse_volume_conv = False
         saved = ops.build_concat_volume, ops.soft_argmin
         ops.build_concat_volume, ops.soft_argmin = torch_concat_volume, torch_soft_argmin
         try:
