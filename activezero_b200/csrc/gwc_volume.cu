@@ -397,6 +397,182 @@ __global__ void __launch_bounds__(kGwcRowThreads) gwc_bwd_row_kernel(const float
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// backward, systolic one-pass kernel (round 2, default).  The direct kernel needs every gradient quad in two
+// alignments (column x for gL, the x + i diagonal for gR: three 128-bit loads per plane, LSU-bound at 0.46 of the
+// HBM peak).  Here a gradient quad g[i][x..x+3] is read ONCE, aligned, and serves both sides:
+//   gL[c][x+j]     += g[i][x+j] * R[c][x+j-i]           (own columns; right window = static register window)
+//   gR[c][x+j-i]   += g[i][x+j] * L[c][x+j]             (own L quad in registers; the TARGET moves, not the data)
+// The accumulator of the target quad Q_k = columns [4k, 4k+4) travels: at step m (planes 4m..4m+3) it sits in the
+// thread t = k + m of the row, takes that thread's contributions with j >= r ("high"), moves one thread to the right
+// (shfl_up; lane 31 -> lane 0 of the next warp through shared memory) and takes the same thread's contributions
+// with j < r ("low").  After ceil(Dq/4) steps thread t holds the finished Q_{t-M}; quads whose walk leaves the row on
+// the right are finished early and written by the row's last thread.  Fixed order, atomic-free, deterministic.
+//
+// Data movement: a CTA owns `rows` = NT/(W/4) whole image rows of one (b, group); its positions are contiguous in
+// every plane, so a gradient plane of the CTA is ONE 1-D bulk async copy (TMA, nact*16 bytes), four planes per stage,
+// kGwcSysStages stages on mbarriers; the feature rows arrive the same way.  Measured (B=8, 136x240, Dq=48, G=8):
+// the kernel is bound by the bytes the stage rings keep in flight (four 128-thread CTAs x 4 stages x 7.7 KB per SM):
+// 3 stages 0.67, 4 stages 0.75, 5 stages (left quads read straight into registers) 0.77 of the HBM peak against 0.46
+// for the direct kernel; 256-thread CTAs 0.73-0.74.  A persistent variant (stage ring running
+// across tiles, features one tile ahead) needs a second right-feature buffer, which costs a stage: 0.69.  An L2
+// prefetch ahead of the ring (cp.async.bulk.prefetch.L2) made it slower (0.51): the extra requests queue in front of
+// the copies the ring waits for.
+// grid = (ceil(H / rows), G, B).
+// ------------------------------------------------------------------------------------------
+
+// LSM: left rows staged in shared memory (S = 4) or read straight into registers (S = 5: their 8 KB buy a stage)
+template <int CPG, int NT, int S, bool LSM>
+__global__ void __launch_bounds__(NT, 512 / NT) gwc_bwd_systolic_kernel(const float* __restrict__ gvol,
+                                                                       const float* __restrict__ L,
+                                                                       const float* __restrict__ R,
+                                                                       float* __restrict__ gL, float* __restrict__ gR,
+                                                                       int C, int G, int H, int W, int Dq, int rows) {
+    extern __shared__ __align__(128) float4 stage[];  // [S][4][NT] | Ls[CPG][NT] | Rs[CPG][NT]
+    __shared__ __align__(8) uint64_t full[S];
+    __shared__ __align__(8) uint64_t feat_bar;
+    __shared__ float4 hand[2][NT / 32 + 1][CPG];  // slot w + 1: lane 31 of warp w; slot 0 stays zero
+    __shared__ float4 zslot;                      // stands in for the planes >= Dq of the last step
+    const int W4 = W >> 2;
+    const int g = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int y0 = blockIdx.x * rows;
+    const int nact = min(rows, H - y0) * W4;  // threads that own a quad
+    const bool active = tid < nact;
+    const int q = tid % W4;
+    const bool row_end = q == W4 - 1;
+    const size_t HW = (size_t)H * W;
+    const size_t p0 = (size_t)y0 * W;  // first float of the CTA's positions within a plane
+    const float* gbase = gvol + ((size_t)b * G + g) * Dq * HW + p0;
+    const size_t cbase = ((size_t)b * C + (size_t)g * CPG) * HW + p0 + (size_t)tid * 4;
+    const int M = (Dq + 3) >> 2;
+    const uint32_t plane_bytes = (uint32_t)nact * 16u;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto issue = [&](int m) {  // one thread: the four planes of step m -> stage m % S
+        const int s = m % S, np = min(4, Dq - 4 * m);
+        mbar_expect_tx(&full[s], plane_bytes * (uint32_t)np);
+        for (int r = 0; r < np; ++r)
+            bulk_g2s(stage + (size_t)(s * 4 + r) * NT, gbase + (size_t)(4 * m + r) * HW, plane_bytes, &full[s]);
+    };
+    float4* Ls = stage + (size_t)S * 4 * NT;
+    float4* Rs = Ls + (LSM ? (size_t)CPG * NT : 0);
+    if (warp == 0) {
+        // lane 0 arms the barriers, then the lanes issue the first copies
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+            mbar_init(&feat_bar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(&feat_bar, plane_bytes * (uint32_t)((LSM ? 2 : 1) * CPG));
+            for (int m = 0; m < min(M, S); ++m)
+                mbar_expect_tx(&full[m], plane_bytes * (uint32_t)min(4, Dq - 4 * m));
+            zslot = zero;
+        }
+        __syncwarp();
+        const size_t fb = ((size_t)b * C + (size_t)g * CPG) * HW + p0;
+        if (lane < 2 * CPG) {
+            const int c = lane >> 1;
+            if (lane & 1) bulk_g2s(Rs + (size_t)c * NT, R + fb + (size_t)c * HW, plane_bytes, &feat_bar);
+            else if (LSM) bulk_g2s(Ls + (size_t)c * NT, L + fb + (size_t)c * HW, plane_bytes, &feat_bar);
+        } else if (lane >= 8 && lane - 8 < min(Dq, 4 * S)) {
+            const int i = lane - 8;  // plane i -> stage i / 4, slot i % 4
+            bulk_g2s(stage + (size_t)i * NT, gbase + (size_t)i * HW, plane_bytes, &full[i >> 2]);
+        }
+    }
+    if (tid < 2 * CPG) hand[tid / CPG][0][tid % CPG] = zero;
+    const float inv = 1.0f / (float)CPG;
+    __syncthreads();  // barrier initialisation, zero slots visible
+    float4 l[CPG], Bw[CPG], aL[CPG], V[CPG];
+    if (!LSM) {
+#pragma unroll
+        for (int c = 0; c < CPG; ++c)
+            l[c] = active ? __ldg(reinterpret_cast<const float4*>(L + cbase + (size_t)c * HW)) : zero;
+    }
+    mbar_wait(&feat_bar, 0);
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) {
+        if (LSM) l[c] = Ls[(size_t)c * NT + tid];  // threads without a quad read stale shared memory: their values never
+        Bw[c] = Rs[(size_t)c * NT + tid];  // reach a thread that owns one (the walk only moves right)
+        aL[c] = zero;
+        V[c] = zero;
+    }
+    const int np_last = Dq - 4 * (M - 1);
+
+#pragma unroll 2
+    for (int m = 0; m < M; ++m) {
+        const int s = m % S;
+        const int np = (m == M - 1) ? np_last : 4;
+        mbar_wait(&full[s], (uint32_t)((m / S) & 1));
+        float4 gq[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) gq[r] = *((r < np) ? stage + (size_t)(s * 4 + r) * NT + tid : &zslot);
+        float4 A[CPG];
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) A[c] = (q - m - 1 >= 0) ? Rs[(size_t)c * NT + tid - m - 1] : zero;
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) {
+            // gL: own columns; gR "high" part: targets j - r >= 0 of the quad this thread holds
+            fma4(aL[c], gq[0], Bw[c]);
+            fma4(V[c], gq[0], l[c]);
+            fma4(aL[c], gq[1], win8(A[c], Bw[c], 3));
+            V[c].x = fmaf(gq[1].y, l[c].y, V[c].x);
+            V[c].y = fmaf(gq[1].z, l[c].z, V[c].y);
+            V[c].z = fmaf(gq[1].w, l[c].w, V[c].z);
+            fma4(aL[c], gq[2], win8(A[c], Bw[c], 2));
+            V[c].x = fmaf(gq[2].z, l[c].z, V[c].x);
+            V[c].y = fmaf(gq[2].w, l[c].w, V[c].y);
+            fma4(aL[c], gq[3], win8(A[c], Bw[c], 1));
+            V[c].x = fmaf(gq[3].w, l[c].w, V[c].x);
+        }
+        if (row_end) {
+            // the walk of Q_{W4-1-m} ends here: finished.  Hand a zero to the first thread of the next row.
+            if (active && q - m >= 0 && gR != nullptr) {
+#pragma unroll
+                for (int c = 0; c < CPG; ++c)
+                    *reinterpret_cast<float4*>(gR + cbase + (size_t)c * HW - (size_t)(4 * m)) =
+                        make_float4(V[c].x * inv, V[c].y * inv, V[c].z * inv, V[c].w * inv);
+            }
+#pragma unroll
+            for (int c = 0; c < CPG; ++c) V[c] = zero;
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int c = 0; c < CPG; ++c) hand[m & 1][warp + 1][c] = V[c];
+        }
+        __syncthreads();  // hand-over slots written; every thread is done with stage s
+        if (tid == 0 && m + S < M) issue(m + S);
+#pragma unroll
+        for (int c = 0; c < CPG; ++c) {
+            float4 rv;
+            rv.x = __shfl_up_sync(0xffffffffu, V[c].x, 1);
+            rv.y = __shfl_up_sync(0xffffffffu, V[c].y, 1);
+            rv.z = __shfl_up_sync(0xffffffffu, V[c].z, 1);
+            rv.w = __shfl_up_sync(0xffffffffu, V[c].w, 1);
+            if (lane == 0) rv = hand[m & 1][warp][c];
+            // gR "low" part of this step: targets 4 + j - r of the quad that has just arrived
+            rv.w = fmaf(gq[1].x, l[c].x, rv.w);
+            rv.z = fmaf(gq[2].x, l[c].x, rv.z);
+            rv.w = fmaf(gq[2].y, l[c].y, rv.w);
+            rv.y = fmaf(gq[3].x, l[c].x, rv.y);
+            rv.z = fmaf(gq[3].y, l[c].y, rv.z);
+            rv.w = fmaf(gq[3].z, l[c].z, rv.w);
+            V[c] = rv;
+            Bw[c] = A[c];
+        }
+    }
+    if (!active) return;
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) {
+        if (gL != nullptr)
+            *reinterpret_cast<float4*>(gL + cbase + (size_t)c * HW) =
+                make_float4(aL[c].x * inv, aL[c].y * inv, aL[c].z * inv, aL[c].w * inv);
+        if (gR != nullptr && q - M >= 0)
+            *reinterpret_cast<float4*>(gR + cbase + (size_t)c * HW - (size_t)(4 * M)) =
+                make_float4(V[c].x * inv, V[c].y * inv, V[c].z * inv, V[c].w * inv);
+    }
+}
+
 // scalar fallback: one thread per (b, c, y, x).  grid = (ceil(H*W/256), C, B)
 __global__ void __launch_bounds__(256) gwc_bwd_scalar_kernel(const float* __restrict__ gvol,
                                                              const float* __restrict__ L, const float* __restrict__ R,
@@ -454,7 +630,28 @@ static int launch_gwc_bwd(const float* gvol, const float* L, const float* R, flo
                           int H, int W, int Dq, cudaStream_t st, bool* done) {
     constexpr int CPT = CPG >= 2 ? 2 : 1;
     *done = false;
-    if (tuning("AZ_GWC_BWD", 0) == 1 && H <= 65535) {  // one-pass row kernel (TMA bulk staging)
+    const int variant = tuning("AZ_GWC_BWD", 2);  // 2 = systolic one-pass (default), 1 = TMA row kernel, 0 = direct
+    if (variant == 2 && CPG <= 4 && W / 4 <= kGwcThreads && G <= 65535) {
+        constexpr int K = CPG <= 4 ? CPG : 1;
+        const int W4 = W / 4;
+        // 128-thread CTAs (four per SM) hide each other's pipeline fill better than two of 256
+        const bool small = W4 <= 128 && tuning("AZ_GWC_BWD_NT", 128) == 128;
+        const bool five = tuning("AZ_GWC_BWD_STAGES", 5) == 5;
+        const int nt = small ? 128 : 256, rows = nt / W4;
+        const int64_t gx = ceil_div(H, rows);
+        if (gx <= 0x7fffffff) {
+            const size_t smem_sys = (size_t)(five ? 5 * 4 + K : 4 * 4 + 2 * K) * nt * sizeof(float4);
+            auto kern = small ? (five ? gwc_bwd_systolic_kernel<K, 128, 5, false> : gwc_bwd_systolic_kernel<K, 128, 4, true>)
+                              : (five ? gwc_bwd_systolic_kernel<K, 256, 5, false> : gwc_bwd_systolic_kernel<K, 256, 4, true>);
+            cudaError_t es = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sys);
+            if (es != cudaSuccess) return (int)es;
+            dim3 grid((unsigned)gx, (unsigned)G, (unsigned)B);
+            kern<<<grid, nt, smem_sys, st>>>(gvol, L, R, gL, gR, C, G, H, W, Dq, rows);
+            *done = true;
+            return (int)cudaGetLastError();
+        }
+    }
+    if (variant == 1 && H <= 65535) {  // one-pass row kernel (TMA bulk staging)
         const int padr = (Dq + 3) / 4 * 4 + 4, GP = (W + Dq + 8 + 3) & ~3;
         const size_t smem_row = ((size_t)(Dq + CPG) * GP + (size_t)CPG * (padr + W)) * sizeof(float);
         if (smem_row <= 200 * 1024 && (size_t)(Dq + 2 * CPG) * W * 4 < (1u << 20)) {

@@ -113,9 +113,9 @@ def main():
             from activezero_b200 import _lib
             from activezero_b200.ops import _ptr, _stream
             gL, gR = torch.empty_like(L), torch.empty_like(R)
-            for v in (0, 1):
-                with env(AZ_GWC_BWD=v):
-                    add("gwc_volume_bwd", f"AZ_GWC_BWD={v}",
+            for v, nt, stg in ((0, 0, 0), (1, 0, 0), (2, 128, 4), (2, 128, 5), (2, 256, 4), (2, 256, 5)):
+                with env(AZ_GWC_BWD=v, AZ_GWC_BWD_NT=nt, AZ_GWC_BWD_STAGES=stg):
+                    add("gwc_volume_bwd", f"AZ_GWC_BWD={v}" + (f",NT={nt},STAGES={stg}" if nt else ""),
                         time_ms(lambda: _lib.call("az_gwc_volume_bwd", _ptr(g), _ptr(L), _ptr(R), _ptr(gL), _ptr(gR), B, C, Hq, Wq,
                                                   Dq, G, _stream()), flush=True), nbb)
         if "vconv" in only:

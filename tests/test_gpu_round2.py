@@ -120,9 +120,12 @@ def test_gwc_reduces_to_pinned_operators():
     close(g8, ref)
 
 
-@pytest.mark.parametrize("knobs", [dict(AZ_GWC_DG=0, AZ_GWC_BWD=0), dict(AZ_GWC_DG=8, AZ_GWC_BWD=1), dict(AZ_GWC_DG=16, AZ_GWC_BWD=1)])
+@pytest.mark.parametrize("knobs", [dict(AZ_GWC_DG=0, AZ_GWC_BWD=0), dict(AZ_GWC_DG=8, AZ_GWC_BWD=1), dict(AZ_GWC_DG=16, AZ_GWC_BWD=1),
+                                   dict(AZ_GWC_DG=16, AZ_GWC_BWD=2), dict(AZ_GWC_BWD=2, AZ_GWC_BWD_NT=256, AZ_GWC_BWD_STAGES=5),
+                                   dict(AZ_GWC_BWD=2, AZ_GWC_BWD_STAGES=5)])
 @pytest.mark.parametrize("shape,dq,G", [((2, 32, 9, 60), 48, 8), ((1, 32, 136, 240), 48, 8), ((1, 16, 7, 36), 13, 16),
-                                        ((1, 8, 5, 24), 30, 2), ((1, 64, 3, 16), 8, 8)])
+                                        ((1, 8, 5, 24), 30, 2), ((1, 64, 3, 16), 8, 8), ((2, 16, 70, 128), 47, 4),
+                                        ((1, 8, 3, 1028), 9, 4), ((1, 4, 37, 4), 6, 4), ((1, 8, 11, 520), 50, 2)])
 def test_gwc_kernel_variants(knobs, shape, dq, G):
     torch.manual_seed(12)
     L = torch.randn(shape, dtype=torch.float64, requires_grad=True)
