@@ -413,8 +413,8 @@ __global__ void __launch_bounds__(kGwcRowThreads) gwc_bwd_row_kernel(const float
 // every plane, so a gradient plane of the CTA is ONE 1-D bulk async copy (TMA, nact*16 bytes), four planes per stage,
 // kGwcSysStages stages on mbarriers; the feature rows arrive the same way.  Measured (B=8, 136x240, Dq=48, G=8):
 // the kernel is bound by the bytes the stage rings keep in flight (four 128-thread CTAs x 4 stages x 7.7 KB per SM):
-// 3 stages 0.67, 4 stages 0.75, 5 stages (left quads read straight into registers) 0.77 of the HBM peak against 0.46
-// for the direct kernel; 256-thread CTAs 0.73-0.74.  A persistent variant (stage ring running
+// 3 stages 0.67, 4 stages 0.75, 5 stages (left quads read straight into registers) 0.77, and 0.80 once the refill
+// copies are spread over four warps, against 0.46 for the direct kernel; 256-thread CTAs 0.73-0.77.  A persistent variant (stage ring running
 // across tiles, features one tile ahead) needs a second right-feature buffer, which costs a stage: 0.69.  An L2
 // prefetch ahead of the ring (cp.async.bulk.prefetch.L2) made it slower (0.51): the extra requests queue in front of
 // the copies the ring waits for.
@@ -541,7 +541,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) gwc_bwd_systolic_kernel(const fl
             for (int c = 0; c < CPG; ++c) hand[m & 1][warp + 1][c] = V[c];
         }
         __syncthreads();  // hand-over slots written; every thread is done with stage s
-        if (tid == 0 && m + S < M) issue(m + S);
+        // refill of the stage just released (step m + S): the arm goes with warp 0, the four plane copies are issued by
+        // lane 0 of warps 0..3, one each -- four copies from ONE thread delay that warp by their issue cost every step
+        // and the other warps then wait for it at the next barrier
+        if (lane == 0 && warp < 4 && m + S < M) {
+            const int mn = m + S, np2 = min(4, Dq - 4 * mn);
+            if (warp == 0) mbar_expect_tx(&full[s], plane_bytes * (uint32_t)np2);
+            if (warp < np2)
+                bulk_g2s(stage + (size_t)(s * 4 + warp) * NT, gbase + (size_t)(4 * mn + warp) * HW, plane_bytes, &full[s]);
+        }
 #pragma unroll
         for (int c = 0; c < CPG; ++c) {
             float4 rv;
