@@ -118,19 +118,22 @@ __global__ void __launch_bounds__(256) warp_fwd4_kernel(const float* __restrict_
 // shared-memory staging: with a single tap per pixel there is nothing to reuse).  One CTA per image row;
 // writes the warped image (same op order as warp_fwd_kernel: bit-identical to the oracle), the pre-gradient
 // and the per-row partial sums consumed by reproj_finalize_kernel.  grid = (H, B), 256 threads.
-__global__ void __launch_bounds__(256, 4) reproj_ps1_kernel(const float* __restrict__ tgt, const float* __restrict__ src,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) reproj_ps1_kernel(const float* __restrict__ tgt, const float* __restrict__ src,
                                                          const float* __restrict__ disp, float sign,
                                                          const uint8_t* __restrict__ mask,
                                                          const float* __restrict__ lin_x,
                                                          const float* __restrict__ lin_y, float* __restrict__ warped,
                                                          float* __restrict__ gpre, double* __restrict__ partial, int C,
                                                          int H, int W) {
-    __shared__ double red[32];
+    __shared__ double red_t[8];
+    __shared__ int red_c[8];
     const int i = blockIdx.x, b = blockIdx.y;
     const int HW = H * W;
     const size_t rowbase = (size_t)b * HW + (size_t)i * W;
     const Axis ay = make_axis(sample_pos(__ldg(lin_y + i), 0.0f, (float)H), H);
-    double tot = 0.0, cnt = 0.0;
+    double tot = 0.0;
+    int cnt = 0;
     for (int j = 4 * threadIdx.x; j < W; j += 4 * 256) {
         float4 d4 = *reinterpret_cast<const float4*>(disp + rowbase + j);
         d4.x *= sign; d4.y *= sign; d4.z *= sign; d4.w *= sign;
@@ -161,15 +164,29 @@ __global__ void __launch_bounds__(256, 4) reproj_ps1_kernel(const float* __restr
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t)
-            if ((m4 >> (8 * t)) & 0xffu) cnt += 1.0;
+            cnt += ((m4 >> (8 * t)) & 0xffu) ? 1 : 0;
         if (gpre != nullptr) *reinterpret_cast<float4*>(gpre + rowbase + j) = make_float4(g[0], g[1], g[2], g[3]);
     }
-    const double bs = block_sum(tot, red);
-    const double bc = block_sum(cnt, red);
+    // one reduction for both: the count is an integer (redux.sync), the sum of squares stays in double; a fixed
+    // order (lanes by xor-shuffle, then warps 0..7) keeps the result run-to-run identical
+    tot = warp_sum(tot);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) {
+        red_t[threadIdx.x >> 5] = tot;
+        red_c[threadIdx.x >> 5] = cnt;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
+        double bs = 0.0;
+        int bc = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            bs += red_t[w];
+            bc += red_c[w];
+        }
         const size_t r = (size_t)b * H + i;
         partial[2 * r] = bs;
-        partial[2 * r + 1] = bc;
+        partial[2 * r + 1] = (double)bc;
     }
 }
 
@@ -718,8 +735,12 @@ extern "C" int az_reproj_loss_fwd(const float* tgt, const float* src, const floa
         (warped == nullptr || aligned16(warped)) && (gpre == nullptr || aligned16(gpre)) &&
         (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 3u) == 0)) {
         dim3 grid((unsigned)H, (unsigned)B);
-        reproj_ps1_kernel<<<grid, 256, 0, st>>>(tgt, src, disp, sign, mask, lin_x, lin_y, warped, gpre, partial, (int)C,
-                                               (int)H, (int)W);
+        if (tuning("AZ_PS1_MINB", 3) == 4)
+            reproj_ps1_kernel<4><<<grid, 256, 0, st>>>(tgt, src, disp, sign, mask, lin_x, lin_y, warped, gpre, partial, (int)C,
+                                                      (int)H, (int)W);
+        else
+            reproj_ps1_kernel<3><<<grid, 256, 0, st>>>(tgt, src, disp, sign, mask, lin_x, lin_y, warped, gpre, partial, (int)C,
+                                                      (int)H, (int)W);
         AZ_LAUNCH_CHECK();
         reproj_finalize_kernel<<<1, 1024, 0, st>>>(partial, B * H, (double)C, loss_out, stats);
         AZ_LAUNCH_CHECK();
