@@ -15,7 +15,10 @@ namespace az {
 
 constexpr int kSWThreads = 256;
 
-// grid = (H, N); smem: W uint32 keys
+// grid = (H, N); smem: W uint32 keys.  SHIFT (W <= 32768): key = (|disp|+1) << 16 | j -- the same order as
+// (|disp|+1) * W + j, unpacked with a mask instead of a 32-bit modulo by a run-time W (ncu at B=8, 544x960: 97
+// instructions per pixel with the multiply / modulo form, issue 65 %).
+template <bool SHIFT>
 __global__ void __launch_bounds__(kSWThreads) scatter_warp_kernel(const float* __restrict__ src,
                                                                  const int32_t* __restrict__ disp,
                                                                  float* __restrict__ dst,
@@ -34,7 +37,7 @@ __global__ void __launch_bounds__(kSWThreads) scatter_warp_kernel(const float* _
         const long long idx = (long long)j + d;
         if (idx >= 0 && idx < W) {
             const uint32_t ad = (uint32_t)(d < 0 ? -d : d);  // < W here
-            atomicMax(&key[(int)idx], (ad + 1u) * (uint32_t)W + (uint32_t)j);
+            atomicMax(&key[(int)idx], SHIFT ? (((ad + 1u) << 16) | (uint32_t)j) : ((ad + 1u) * (uint32_t)W + (uint32_t)j));
         }
     }
     if (sign_flags != nullptr) {
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(kSWThreads) scatter_warp_kernel(const float* _
         float* orow = dst + ((size_t)n * C + c) * HW + (size_t)y * W;
         for (int x = threadIdx.x; x < W; x += kSWThreads) {
             const uint32_t k = key[x];
-            orow[x] = k != 0u ? __ldg(srow + (k % (uint32_t)W)) : 0.f;
+            orow[x] = k != 0u ? __ldg(srow + (SHIFT ? (k & 0xffffu) : (k % (uint32_t)W))) : 0.f;
         }
     }
 }
@@ -62,14 +65,17 @@ extern "C" int az_scatter_warp(const float* src, const int32_t* disp, float* dst
     // key packing needs (W+1)*W < 2^32; smem row of W keys
     if (W > 46340 || N > 65535 || W * 4 > 200 * 1024) return AZ_ERR_BAD_ARG;
     const size_t smem = (size_t)W * sizeof(uint32_t);
+    const bool shift = W <= 32768 && tuning("AZ_SCATTER_SHIFT", 1) != 0;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(scatter_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(shift ? scatter_warp_kernel<true> : scatter_warp_kernel<false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
     dim3 grid((unsigned)H, (unsigned)N);
-    scatter_warp_kernel<<<grid, kSWThreads, smem, (cudaStream_t)stream>>>(src, disp, dst, sign_flags, (int)C, (int)H,
-                                                                        (int)W);
+    if (shift)
+        scatter_warp_kernel<true><<<grid, kSWThreads, smem, (cudaStream_t)stream>>>(src, disp, dst, sign_flags, (int)C, (int)H, (int)W);
+    else
+        scatter_warp_kernel<false><<<grid, kSWThreads, smem, (cudaStream_t)stream>>>(src, disp, dst, sign_flags, (int)C, (int)H, (int)W);
     AZ_LAUNCH_CHECK();
     return 0;
 }

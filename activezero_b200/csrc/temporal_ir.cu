@@ -103,10 +103,25 @@ constexpr int kTirTX = 32, kTirTY = 8;  // tile of the generic LCN fallback belo
 //   ks^2 a - boxsum > thr ks^2 R  (left side exact in int64, right side one double product per image).
 constexpr int kTpTW = 64, kTpTH = 32;
 
+// KS > 0: window size known at compile time (tile extents and the divisions by them become constants); KS = 0: run-time ks.
+// Round 2 (ncu at B=8, 544x960: 183 instructions per pixel, 63 % of them in the tile fill, issue 73 %): the fill divides
+// by a compile-time tile width, reflects with one step per side (valid whenever the image is larger than the halo; tiny
+// images take the loop) and keeps four independent gathers in flight per thread, instead of two run-time divisions and
+// two reflection loops per halo element with one load in flight.
+__device__ __forceinline__ int reflect101_fast(int i, int n, bool simple) {
+    if (simple) {  // n > halo: at most one reflection on either side
+        i = i < 0 ? -i : i;
+        return i >= n ? 2 * n - 2 - i : i;
+    }
+    return reflect101(i, n);
+}
+
+template <int KS>
 __global__ void __launch_bounds__(256) tir_pattern_kernel(const int* __restrict__ ain, const int* __restrict__ minmax,
-                                                          float* __restrict__ pattern, int H, int W, int ks,
+                                                          float* __restrict__ pattern, int H, int W, int ks_rt,
                                                           double threshold) {
     extern __shared__ int itile[];
+    const int ks = KS > 0 ? KS : ks_rt;
     const int h = ks >> 1;
     const int IW = kTpTW + ks - 1, IH = kTpTH + ks - 1;
     int* rows = itile + IW * IH;  // [IH][TW] horizontal window sums
@@ -115,17 +130,30 @@ __global__ void __launch_bounds__(256) tir_pattern_kernel(const int* __restrict_
     const double rhs = threshold * (double)(ks * ks) * (double)(minmax[2 * b + 1] - minmax[2 * b]);
     const int* d = ain + (size_t)b * H * W;
     const int tid = threadIdx.x;
-    for (int t = tid; t < IW * IH; t += 256) {
-        const int ty = t / IW, tx = t - ty * IW;
-        const int yy = reflect101(y0 + ty - h, H), xx = reflect101(x0 + tx - h, W);
-        itile[t] = __ldg(d + (size_t)yy * W + xx);
+    const bool simple = H > h && W > h;
+    // four independent gathers in flight per thread (the divisions are by a compile-time IW when KS > 0)
+    for (int t0 = tid; t0 < IW * IH; t0 += 4 * 256) {
+        int v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * 256;
+            const int ty = t / IW, tx = t - ty * IW;
+            const int yy = reflect101_fast(y0 + ty - h, H, simple), xx = reflect101_fast(x0 + tx - h, W, simple);
+            v[u] = t < IW * IH ? __ldg(d + (size_t)yy * W + xx) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (t0 + u * 256 < IW * IH) itile[t0 + u * 256] = v[u];
     }
     __syncthreads();
     for (int it = tid; it < IH * (kTpTW / 8); it += 256) {
         const int ty = it / (kTpTW / 8), xl = 8 * (it - ty * (kTpTW / 8));
         const int* r = itile + ty * IW + xl;
         int s = 0;
-        for (int k = 0; k < ks; ++k) s += r[k];
+#pragma unroll
+        for (int k = 0; k < (KS > 0 ? KS : 1); ++k) s += r[k];
+        if (KS == 0)
+            for (int k = 1; k < ks; ++k) s += r[k];
         int* o = rows + ty * kTpTW + xl;
         o[0] = s;
 #pragma unroll
@@ -139,7 +167,10 @@ __global__ void __launch_bounds__(256) tir_pattern_kernel(const int* __restrict_
     const int x = x0 + c;
     if (x >= W) return;
     long long s = 0;
-    for (int k = 0; k < ks; ++k) s += rows[(r0 + k) * kTpTW + c];
+#pragma unroll
+    for (int k = 0; k < (KS > 0 ? KS : 1); ++k) s += rows[(r0 + k) * kTpTW + c];
+    if (KS == 0)
+        for (int k = 1; k < ks; ++k) s += rows[(r0 + k) * kTpTW + c];
     const long long k2 = (long long)ks * ks;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -181,10 +212,23 @@ __global__ void __launch_bounds__(256) lcn_sep_kernel(const float* __restrict__ 
     const int x0 = blockIdx.x * kLsTW, y0 = blockIdx.y * kLsTH;
     const float* im = image + (size_t)b * Cin * H * W;  // channel 0 (reprojection.py:184-185)
     const int tid = threadIdx.x;
-    for (int t = tid; t < IH * kLsIW; t += 256) {
-        const int ty = t / kLsIW, tx = t - ty * kLsIW;
-        const int yy = y0 + ty - h, xx = x0 + tx - h;
-        tile[t] = (tx < IWU && yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + (size_t)yy * W + xx) : 0.f;
+    if ((h & 3) == 0 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(im) & 15u) == 0) {
+        // kernel_size 9 (the reference's default): the tile's first column x0 - 4 is 16-byte aligned, a quad is wholly
+        // inside or wholly outside the row -> 128-bit loads, one quarter of the load instructions
+        constexpr int Q = (IWU + 3) / 4;
+        for (int t = tid; t < IH * Q; t += 256) {
+            const int ty = t / Q, q = t - ty * Q;
+            const int yy = y0 + ty - h, xx = x0 - h + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(reinterpret_cast<const float4*>(im + (size_t)yy * W + xx));
+            *reinterpret_cast<float4*>(tile + ty * kLsIW + 4 * q) = v;
+        }
+    } else {
+        for (int t = tid; t < IH * kLsIW; t += 256) {
+            const int ty = t / kLsIW, tx = t - ty * kLsIW;
+            const int yy = y0 + ty - h, xx = x0 + tx - h;
+            tile[t] = (tx < IWU && yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + (size_t)yy * W + xx) : 0.f;
+        }
     }
     __syncthreads();
     for (int it = tid; it < IH * (kLsTW / 4); it += 256) {
@@ -318,12 +362,16 @@ extern "C" int az_temporal_ir(const uint8_t* frames, float* pattern, void* works
     AZ_LAUNCH_CHECK();
     const int IW = kTpTW + (int)ks - 1, IH = kTpTH + (int)ks - 1;
     const size_t smem = ((size_t)IW * IH + (size_t)IH * kTpTW) * sizeof(int);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(tir_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
     dim3 g2((unsigned)ceil_div(W, kTpTW), (unsigned)ceil_div(H, kTpTH), (unsigned)B);
-    tir_pattern_kernel<<<g2, 256, smem, st>>>(diff, minmax, pattern, (int)H, (int)W, (int)ks, threshold);
+    if (ks == 11 && tuning("AZ_TIR_KS_TEMPLATE", 1) != 0) {  // tools/temporal_ir.py's window
+        tir_pattern_kernel<11><<<g2, 256, smem, st>>>(diff, minmax, pattern, (int)H, (int)W, (int)ks, threshold);
+    } else {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(tir_pattern_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        tir_pattern_kernel<0><<<g2, 256, smem, st>>>(diff, minmax, pattern, (int)H, (int)W, (int)ks, threshold);
+    }
     AZ_LAUNCH_CHECK();
     return 0;
 }
