@@ -32,9 +32,12 @@ __global__ void __launch_bounds__(256) tir_init_kernel(int* __restrict__ minmax,
 }
 
 // grid = (ceil(H*W/V/256), B); a thread owns V adjacent pixels (V = 4: one 32-bit load per frame, one 128-bit store)
-template <int V>
+// TT > 0: the frame count at compile time (7 in tools/temporal_ir.py:64-70): the T loads are issued back to back and the
+// weights 2t - (T-1) are immediates (ncu, run-time T: 62 instructions per pixel, issue 67 %); TT = 0: run-time T.
+template <int V, int TT>
 __global__ void __launch_bounds__(256) tir_slope_kernel(const uint8_t* __restrict__ frames, int* __restrict__ aout,
-                                                        int* __restrict__ minmax, int T, int64_t HW) {
+                                                        int* __restrict__ minmax, int T_rt, int64_t HW) {
+    const int T = TT > 0 ? TT : T_rt;
     const int64_t p = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V;
     const int b = blockIdx.y;
     int mn = 0x7fffffff, mx = 0;
@@ -43,13 +46,24 @@ __global__ void __launch_bounds__(256) tir_slope_kernel(const uint8_t* __restric
         int acc[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = 0;
-        for (int t = 0; t < T; ++t) {
-            const int wgt = 2 * t - (T - 1);
-            if (V == 4) {
-                const uchar4 q = *reinterpret_cast<const uchar4*>(f + (size_t)t * HW);
-                acc[0] += wgt * (int)q.x; acc[1 % V] += wgt * (int)q.y; acc[2 % V] += wgt * (int)q.z; acc[3 % V] += wgt * (int)q.w;
-            } else {
-                acc[0] += wgt * (int)f[(size_t)t * HW];
+        if (TT > 0 && V == 4) {
+            uchar4 q[TT > 0 ? TT : 1];
+#pragma unroll
+            for (int t = 0; t < TT; ++t) q[t] = __ldg(reinterpret_cast<const uchar4*>(f + (size_t)t * HW));
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                const int wgt = 2 * t - (TT - 1);
+                acc[0] += wgt * (int)q[t].x; acc[1 % V] += wgt * (int)q[t].y; acc[2 % V] += wgt * (int)q[t].z; acc[3 % V] += wgt * (int)q[t].w;
+            }
+        } else {
+            for (int t = 0; t < T; ++t) {
+                const int wgt = 2 * t - (T - 1);
+                if (V == 4) {
+                    const uchar4 q = *reinterpret_cast<const uchar4*>(f + (size_t)t * HW);
+                    acc[0] += wgt * (int)q.x; acc[1 % V] += wgt * (int)q.y; acc[2 % V] += wgt * (int)q.z; acc[3 % V] += wgt * (int)q.w;
+                } else {
+                    acc[0] += wgt * (int)f[(size_t)t * HW];
+                }
             }
         }
 #pragma unroll
@@ -62,11 +76,8 @@ __global__ void __launch_bounds__(256) tir_slope_kernel(const uint8_t* __restric
         if (V == 4) *reinterpret_cast<int4*>(o) = make_int4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
         else o[0] = acc[0];
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
+    mn = __reduce_min_sync(0xffffffffu, mn);  // redux.sync: one instruction each
+    mx = __reduce_max_sync(0xffffffffu, mx);
     // one atomic pair per CTA (per-warp atomics on the 2 words of an image serialise in L2: 130 k of them at 544x960)
     __shared__ int smn[8], smx[8];
     if ((threadIdx.x & 31) == 0) {
@@ -109,46 +120,108 @@ constexpr int kTpTW = 64, kTpTH = 32;
 // images take the loop) and keeps four independent gathers in flight per thread, instead of two run-time divisions and
 // two reflection loops per halo element with one load in flight.
 __device__ __forceinline__ int reflect101_fast(int i, int n, bool simple) {
-    if (simple) {  // n > halo: at most one reflection on either side
+    if (simple) {  // n > halo: one reflection on either side is exact for every index a written pixel uses
         i = i < 0 ? -i : i;
-        return i >= n ? 2 * n - 2 - i : i;
+        i = i >= n ? 2 * n - 2 - i : i;
+        return min(max(i, 0), n - 1);  // tile cells far beyond the image (unused) still read inside it
     }
     return reflect101(i, n);
 }
 
-template <int KS>
+// VEC (W % 4 == 0, 16-byte aligned `ain`): the tile's 64 own columns are filled with 128-bit loads and stores (the tile
+// is laid out so that they start at a multiple of four: OFFX leading pad columns), only the 2h halo columns and quads
+// that touch the right image border go through the per-element reflection.
+template <int KS, bool VEC>
 __global__ void __launch_bounds__(256) tir_pattern_kernel(const int* __restrict__ ain, const int* __restrict__ minmax,
                                                           float* __restrict__ pattern, int H, int W, int ks_rt,
                                                           double threshold) {
-    extern __shared__ int itile[];
+    extern __shared__ __align__(16) int itile[];
     const int ks = KS > 0 ? KS : ks_rt;
     const int h = ks >> 1;
+    const int OFFX = ((h + 3) & ~3) - h;                        // pad columns in front of the tile
     const int IW = kTpTW + ks - 1, IH = kTpTH + ks - 1;
-    int* rows = itile + IW * IH;  // [IH][TW] horizontal window sums
+    const int IWP = (OFFX + IW + 3) & ~3;                       // row pitch (multiple of 4)
+    int* rows = itile + IWP * IH;  // [IH][TW] horizontal window sums
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH;
+    // lhs > rhs with an integer lhs  <=>  lhs >= floor(rhs) + 1: one integer compare per pixel instead of an
+    // int64 -> double conversion (NaN / +inf: nothing passes, as with the floating-point compare)
     const double rhs = threshold * (double)(ks * ks) * (double)(minmax[2 * b + 1] - minmax[2 * b]);
+    long long thr;
+    if (!(rhs < 9.0e18)) thr = 0x7fffffffffffffffll;
+    else if (rhs < -9.0e18) thr = -0x7fffffffffffffffll - 1;
+    else thr = (long long)floor(rhs) + 1;
+    const bool never = !(rhs < 9.0e18);
     const int* d = ain + (size_t)b * H * W;
     const int tid = threadIdx.x;
     const bool simple = H > h && W > h;
-    // four independent gathers in flight per thread (the divisions are by a compile-time IW when KS > 0)
-    for (int t0 = tid; t0 < IW * IH; t0 += 4 * 256) {
-        int v[4];
+    if (VEC) {
+        // items of a tile row: 16 quads (own columns) then 2h halo columns
+        const int per_row = kTpTW / 4 + 2 * h;
+        for (int t0 = tid; t0 < per_row * IH; t0 += 2 * 256) {
+            int4 v[2];
+            int sc[2];
+            int dst[2];
+            bool isq[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int t = t0 + u * 256;
-            const int ty = t / IW, tx = t - ty * IW;
-            const int yy = reflect101_fast(y0 + ty - h, H, simple), xx = reflect101_fast(x0 + tx - h, W, simple);
-            v[u] = t < IW * IH ? __ldg(d + (size_t)yy * W + xx) : 0;
+            for (int u = 0; u < 2; ++u) {
+                const int t = t0 + u * 256;
+                const int ty = t / per_row, it = t - ty * per_row;
+                const int yy = reflect101_fast(y0 + ty - h, H, simple);
+                const int* srow = d + (size_t)yy * W;
+                dst[u] = -1;
+                isq[u] = false;
+                if (t < per_row * IH) {
+                    if (it < kTpTW / 4) {
+                        const int xx = x0 + 4 * it;
+                        dst[u] = ty * IWP + OFFX + h + 4 * it;
+                        isq[u] = true;
+                        if (xx + 3 < W) {
+                            v[u] = __ldg(reinterpret_cast<const int4*>(srow + xx));
+                        } else {  // beyond the right border: reflected, element by element
+                            v[u].x = __ldg(srow + reflect101_fast(xx, W, simple));
+                            v[u].y = __ldg(srow + reflect101_fast(xx + 1, W, simple));
+                            v[u].z = __ldg(srow + reflect101_fast(xx + 2, W, simple));
+                            v[u].w = __ldg(srow + reflect101_fast(xx + 3, W, simple));
+                        }
+                    } else {
+                        const int k = it - kTpTW / 4;                       // 0 .. 2h-1
+                        const int tx = k < h ? k : kTpTW + k;               // left halo, right halo
+                        dst[u] = ty * IWP + OFFX + tx;
+                        sc[u] = __ldg(srow + reflect101_fast(x0 + tx - h, W, simple));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (dst[u] >= 0) {
+                    if (isq[u]) *reinterpret_cast<int4*>(itile + dst[u]) = v[u];
+                    else itile[dst[u]] = sc[u];
+                }
+            }
         }
+    } else {
+        // four independent gathers in flight per thread (the divisions are by a compile-time IW when KS > 0)
+        for (int t0 = tid; t0 < IW * IH; t0 += 4 * 256) {
+            int v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (t0 + u * 256 < IW * IH) itile[t0 + u * 256] = v[u];
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + u * 256;
+                const int ty = t / IW, tx = t - ty * IW;
+                const int yy = reflect101_fast(y0 + ty - h, H, simple), xx = reflect101_fast(x0 + tx - h, W, simple);
+                v[u] = t < IW * IH ? __ldg(d + (size_t)yy * W + xx) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + u * 256;
+                if (t < IW * IH) itile[(t / IW) * IWP + OFFX + (t - (t / IW) * IW)] = v[u];
+            }
+        }
     }
     __syncthreads();
     for (int it = tid; it < IH * (kTpTW / 8); it += 256) {
         const int ty = it / (kTpTW / 8), xl = 8 * (it - ty * (kTpTW / 8));
-        const int* r = itile + ty * IW + xl;
+        const int* r = itile + ty * IWP + OFFX + xl;
         int s = 0;
 #pragma unroll
         for (int k = 0; k < (KS > 0 ? KS : 1); ++k) s += r[k];
@@ -172,12 +245,13 @@ __global__ void __launch_bounds__(256) tir_pattern_kernel(const int* __restrict_
     if (KS == 0)
         for (int k = 1; k < ks; ++k) s += rows[(r0 + k) * kTpTW + c];
     const long long k2 = (long long)ks * ks;
+    float* prow = pattern + (size_t)b * H * W + (size_t)(y0 + r0) * W + x;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int y = y0 + r0 + r;
         if (y < H) {
-            const long long lhs = k2 * (long long)itile[(r0 + r + h) * IW + c + h] - s;
-            pattern[(size_t)b * H * W + (size_t)y * W + x] = ((double)lhs > rhs) ? 1.0f : 0.0f;
+            const long long lhs = k2 * (long long)itile[(r0 + r + h) * IWP + OFFX + c + h] - s;
+            prow[(size_t)r * W] = (!never && lhs >= thr) ? 1.0f : 0.0f;
         }
         if (r < 7) s += rows[(r0 + r + ks) * kTpTW + c] - rows[(r0 + r) * kTpTW + c];
     }
@@ -354,23 +428,29 @@ extern "C" int az_temporal_ir(const uint8_t* frames, float* pattern, void* works
     AZ_LAUNCH_CHECK();
     if (HW % 4 == 0 && (reinterpret_cast<uintptr_t>(frames) & 3u) == 0 && aligned16(workspace)) {
         dim3 g1((unsigned)ceil_div(HW / 4, 256), (unsigned)B);
-        tir_slope_kernel<4><<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
+        if (T == 7) tir_slope_kernel<4, 7><<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
+        else if (T == 4) tir_slope_kernel<4, 4><<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
+        else tir_slope_kernel<4, 0><<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
     } else {
         dim3 g1((unsigned)ceil_div(HW, 256), (unsigned)B);
-        tir_slope_kernel<1><<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
+        tir_slope_kernel<1, 0><<<g1, 256, 0, st>>>(frames, diff, minmax, (int)T, HW);
     }
     AZ_LAUNCH_CHECK();
-    const int IW = kTpTW + (int)ks - 1, IH = kTpTH + (int)ks - 1;
-    const size_t smem = ((size_t)IW * IH + (size_t)IH * kTpTW) * sizeof(int);
+    const int hh = (int)(ks >> 1), OFFX = ((hh + 3) & ~3) - hh;
+    const int IW = kTpTW + (int)ks - 1, IH = kTpTH + (int)ks - 1, IWP = (OFFX + IW + 3) & ~3;
+    const size_t smem = ((size_t)IWP * IH + (size_t)IH * kTpTW) * sizeof(int);
     dim3 g2((unsigned)ceil_div(W, kTpTW), (unsigned)ceil_div(H, kTpTH), (unsigned)B);
+    const bool vec = W % 4 == 0 && aligned16(workspace) && tuning("AZ_TIR_VEC", 1) != 0;
     if (ks == 11 && tuning("AZ_TIR_KS_TEMPLATE", 1) != 0) {  // tools/temporal_ir.py's window
-        tir_pattern_kernel<11><<<g2, 256, smem, st>>>(diff, minmax, pattern, (int)H, (int)W, (int)ks, threshold);
+        if (vec) tir_pattern_kernel<11, true><<<g2, 256, smem, st>>>(diff, minmax, pattern, (int)H, (int)W, (int)ks, threshold);
+        else tir_pattern_kernel<11, false><<<g2, 256, smem, st>>>(diff, minmax, pattern, (int)H, (int)W, (int)ks, threshold);
     } else {
+        auto kern = vec ? tir_pattern_kernel<0, true> : tir_pattern_kernel<0, false>;
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(tir_pattern_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
         }
-        tir_pattern_kernel<0><<<g2, 256, smem, st>>>(diff, minmax, pattern, (int)H, (int)W, (int)ks, threshold);
+        kern<<<g2, 256, smem, st>>>(diff, minmax, pattern, (int)H, (int)W, (int)ks, threshold);
     }
     AZ_LAUNCH_CHECK();
     return 0;
