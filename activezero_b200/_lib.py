@@ -50,6 +50,7 @@ SIGNATURES = {
     "az_bilinear_rescale_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P]),
     "az_bilinear_rescale_bwd": (ctypes.c_int, [_P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P]),
     "az_scatter_warp": (ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "az_scatter_warp_gt": (ctypes.c_int, [_P, _P, _P, _P, _F, _I, _I, _I, _P]),
     "az_temporal_ir_workspace_bytes": (_I, [_I, _I, _I]),
     "az_temporal_ir": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _D, _P]),
     "az_sim_ir_pattern_workspace_bytes": (_I, [_I, _I, _I, _I]),

@@ -55,6 +55,54 @@ __global__ void __launch_bounds__(kSWThreads) scatter_warp_kernel(const float* _
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The trainer's ground-truth chain in ONE launch (SURVEY.md §8a row a10's caller, /root/reference/train.py:255-272,
+// test.py:109-110): the right-view disparity arrives at twice the working resolution, is halved with
+// F.interpolate(scale_factor=0.5, mode="nearest") (= source pixel (2y, 2j)), truncated to int32 (`.type(torch.int)`),
+// scatter-warped onto the left view with ITSELF as the payload (apply_disparity_cu(img_disp_r, img_disp_r.int())) and
+// thresholded into the training mask (0 < disp_gt_l < max_disp).  The reference spends an interpolate, a cast, the
+// scatter warp, two comparisons and a product (six launches, five HxW temporaries); here a CTA reads every other pixel
+// of one source row, races the keys in shared memory and writes the warped disparity and the mask.
+// grid = (H, N), H = H2 / 2, W = W2 / 2; smem: W keys + W values.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSWThreads) scatter_warp_gt_kernel(const float* __restrict__ disp2x,
+                                                                    float* __restrict__ disp_out,
+                                                                    uint8_t* __restrict__ mask_out,
+                                                                    int32_t* __restrict__ sign_flags, float max_disp,
+                                                                    int H2, int W2, int H, int W) {
+    extern __shared__ uint32_t key[];
+    float* val = reinterpret_cast<float*>(key + W);
+    const int y = blockIdx.x, n = blockIdx.y;
+    const float* srow = disp2x + ((size_t)n * H2 + 2 * (size_t)y) * W2;
+    for (int j = threadIdx.x; j < W; j += kSWThreads) {
+        key[j] = 0u;
+        val[j] = __ldg(srow + 2 * j);
+    }
+    __syncthreads();
+    int flags = 0;
+    for (int j = threadIdx.x; j < W; j += kSWThreads) {
+        const int d = __float2int_rz(val[j]);  // .type(torch.int): truncation toward zero
+        flags |= (d > 0 ? 1 : 0) | (d < 0 ? 2 : 0);
+        const long long idx = (long long)j + d;
+        if (idx >= 0 && idx < W) {
+            const uint32_t ad = (uint32_t)(d < 0 ? -d : d);  // < W here
+            atomicMax(&key[(int)idx], ((ad + 1u) << 16) | (uint32_t)j);
+        }
+    }
+    if (sign_flags != nullptr) {
+        flags = __reduce_or_sync(0xffffffffu, flags);
+        if ((threadIdx.x & 31) == 0 && flags != 0) atomicOr(sign_flags, flags);
+    }
+    __syncthreads();
+    const size_t obase = ((size_t)n * H + y) * W;
+    for (int x = threadIdx.x; x < W; x += kSWThreads) {
+        const uint32_t k = key[x];
+        const float v = k != 0u ? val[k & 0xffffu] : 0.f;
+        disp_out[obase + x] = v;
+        if (mask_out != nullptr) mask_out[obase + x] = (v < max_disp && v > 0.f) ? 1 : 0;
+    }
+}
+
 }  // namespace az
 
 using namespace az;
@@ -76,6 +124,23 @@ extern "C" int az_scatter_warp(const float* src, const int32_t* disp, float* dst
         scatter_warp_kernel<true><<<grid, kSWThreads, smem, (cudaStream_t)stream>>>(src, disp, dst, sign_flags, (int)C, (int)H, (int)W);
     else
         scatter_warp_kernel<false><<<grid, kSWThreads, smem, (cudaStream_t)stream>>>(src, disp, dst, sign_flags, (int)C, (int)H, (int)W);
+    AZ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int az_scatter_warp_gt(const float* disp2x, float* disp_out, uint8_t* mask_out, int32_t* sign_flags,
+                                  float max_disp, int64_t N, int64_t H2, int64_t W2, void* stream) {
+    if (!disp2x || !disp_out || N <= 0 || H2 < 2 || W2 < 2) return AZ_ERR_BAD_ARG;
+    const int64_t H = H2 / 2, W = W2 / 2;  // floor(size * 0.5), F.interpolate with recompute_scale_factor=False
+    if (W > 32768 || N > 65535 || H * W >= (1ll << 31) || H2 * W2 >= (1ll << 31)) return AZ_ERR_BAD_ARG;
+    const size_t smem = (size_t)W * 2 * sizeof(uint32_t);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(scatter_warp_gt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid((unsigned)H, (unsigned)N);
+    scatter_warp_gt_kernel<<<grid, kSWThreads, smem, (cudaStream_t)stream>>>(disp2x, disp_out, mask_out, sign_flags, max_disp,
+                                                                          (int)H2, (int)W2, (int)H, (int)W);
     AZ_LAUNCH_CHECK();
     return 0;
 }

@@ -496,6 +496,28 @@ def scatter_warp(img, disp, check_sign: bool = True):
     return out
 
 
+def scatter_warp_gt(disp_r_2x, max_disp: float, check_sign: bool = True):
+    """The trainer's ground-truth chain in one launch (/root/reference/train.py:255-272): nearest x0.5 of the
+    double-resolution right-view disparity, ``.type(torch.int)``, ``apply_disparity_cu`` with the disparity as its own
+    payload, and the mask ``0 < disp_gt_l < max_disp``.  [N,1,2H,2W] float32 -> (disp_gt_l [N,1,H,W] float32,
+    mask [N,1,H,W] bool)."""
+    if not isinstance(disp_r_2x, torch.Tensor) or not disp_r_2x.is_cuda or disp_r_2x.dtype != torch.float32:
+        raise ValueError("scatter_warp_gt: expected a float32 CUDA tensor")
+    if disp_r_2x.dim() != 4 or disp_r_2x.shape[1] != 1 or disp_r_2x.shape[2] < 2 or disp_r_2x.shape[3] < 2:
+        raise ValueError("scatter_warp_gt: expected [N,1,2H,2W]")
+    d = disp_r_2x.contiguous()
+    N, _, H2, W2 = d.shape
+    H, W = H2 // 2, W2 // 2
+    out = torch.empty((N, 1, H, W), dtype=torch.float32, device=d.device)
+    mask = torch.empty((N, 1, H, W), dtype=torch.uint8, device=d.device)
+    flags = torch.zeros((1,), dtype=torch.int32, device=d.device) if check_sign else None
+    with torch.cuda.device(d.device):
+        _lib.call("az_scatter_warp_gt", _ptr(d), _ptr(out), _ptr(mask), _ptr(flags), float(max_disp), N, H2, W2, _stream())
+    if check_sign:
+        assert int(flags.item()) != 3, "disparities must be all >= 0 or all <= 0"
+    return out, mask.view(torch.bool)
+
+
 def temporal_ir_pattern(frames, ks: int = 11, threshold: float = 0.005):
     """[B,T,H,W] or [T,H,W] uint8 -> [B,H,W] / [H,W] float32 {0,1}
     (tools/temporal_ir.py:93-114)."""

@@ -17,3 +17,14 @@ def apply_disparity_cu(img: torch.Tensor, disp: torch.Tensor):
     :return: warped tensor like ``img``; un-hit pixels are 0
     """
     return ops.scatter_warp(img, disp, check_sign=True)
+
+
+def disp_gt_from_right_view(img_disp_r_2x: torch.Tensor, max_disp: float):
+    """Opt-in replacement of the twelve lines around ``apply_disparity_cu`` in the trainer
+    (``/root/reference/train.py:255-272``; same chain in ``test.py:109-110``): the double-resolution right-view
+    disparity -> nearest x0.5 -> ``.type(torch.int)`` -> scatter warp of the disparity by itself -> training mask.
+
+    :param img_disp_r_2x: (N, 1, 2H, 2W) float32, what ``sample["img_disp_R"]`` holds
+    :return: ``(disp_gt_l (N,1,H,W) float32, mask (N,1,H,W) bool)`` -- identical to the reference chain
+    """
+    return ops.scatter_warp_gt(img_disp_r_2x, max_disp, check_sign=True)

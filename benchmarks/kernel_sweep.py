@@ -186,6 +186,17 @@ def sweep(quick):
                                                          flush=True, graph=True), 4 * 4 * hw + hw)
         di = (torch.rand(B, 1, H, W, device=DEV) * 64).int()
         add("scatter_warp", cfg, time_ms(lambda: ops.scatter_warp(d, di, check_sign=False), flush=True, graph=True), 4 * 3 * hw)
+        # the trainer's GT chain (train.py:255-272) fused, against the reference's six calls on this library's scatter warp
+        d2x = torch.rand(B, 1, 2 * H, 2 * W, device=DEV) * 100
+
+        def gt_unfused():
+            r = torch.nn.functional.interpolate(d2x, scale_factor=0.5, mode="nearest", recompute_scale_factor=False)
+            o = ops.scatter_warp(r, r.type(torch.int), check_sign=False)
+            return o, (o < 192) * (o > 0)
+
+        nb_gt = hw * (4 + 4 + 1)  # the quarter of the 2x image that is read + disparity out + mask out
+        add("gt_chain_fused", cfg, time_ms(lambda: ops.scatter_warp_gt(d2x, 192.0, check_sign=False), flush=True, graph=True), nb_gt)
+        add("context:gt_chain_unfused(torch interpolate+cast+az scatter+mask)", cfg, time_ms(gt_unfused, flush=True, graph=True), nb_gt)
         add("local_contrast_norm", cfg, time_ms(lambda: ops.local_contrast_norm(pL, 9), flush=True, graph=True), 4 * 3 * hw)
         T = 7
         fr = torch.randint(0, 255, (B, T, H, W), dtype=torch.uint8, device=DEV)

@@ -159,6 +159,15 @@ int az_bilinear_rescale_bwd(const float* gout, float* gin, int64_t B, int64_t H,
 int az_scatter_warp(const float* src, const int32_t* disp, float* dst, int32_t* sign_flags,
                     int64_t N, int64_t C, int64_t H, int64_t W, void* stream);
 
+/* The trainer's ground-truth chain around a10 in one launch -- /root/reference/train.py:255-272 (test.py:109-110):
+ *   r   = F.interpolate(disp2x, scale_factor=0.5, mode="nearest")        (source pixel (2y, 2j); H = H2/2, W = W2/2)
+ *   out = apply_disparity_cu(r, r.type(torch.int))                       (the payload is the disparity itself)
+ *   mask = (out < max_disp) * (out > 0)                                  (train.py:272)
+ * disp2x: [N,1,H2,W2] float32; disp_out: [N,1,H,W] float32; mask_out: [N,1,H,W] uint8 (0/1) or NULL;
+ * sign_flags as in az_scatter_warp. */
+int az_scatter_warp_gt(const float* disp2x, float* disp_out, uint8_t* mask_out, int32_t* sign_flags,
+                       float max_disp, int64_t N, int64_t H2, int64_t W2, void* stream);
+
 /* ---- a11: temporal IR pattern -- tools/temporal_ir.py:35-40, 93-114 ----
  * frames: [B,T,H,W] uint8 -> pattern [B,H,W] float32 in {0,1}: per-pixel least-squares slope over t,
  * |fit[T-1]-fit[0]|/255, per-image min-max normalise, minus ks x ks box blur (BORDER_REFLECT_101),

@@ -488,3 +488,25 @@ def test_volume_conv0_epilogue_and_psmnet_flag():
         p_fused = net(a, b)
     assert p_fused.shape == p_ref.shape and torch.isfinite(p_fused).all()
     assert float(p_fused.min()) >= 0.0 and float(p_fused.max()) <= 191.0
+
+
+# --------------------------------------------------------------------------- a10's caller: the trainer's GT chain, fused
+@pytest.mark.parametrize("shape", [(2, 1, 64, 128), (1, 1, 1088, 1920), (3, 1, 7, 10), (1, 1, 2, 2), (1, 1, 33, 65)])
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_gt_chain_matches_reference_chain(shape, sign):
+    """train.py:255-272: interpolate(nearest, 0.5) -> .type(int) -> apply_disparity_cu(r, r.int()) -> mask, as the
+    reference spells it (torch's interpolate, the oracle's scatter warp = the reference kernel semantics) against the
+    fused launch: bit-exact disparity, identical mask; zeros (holes in the rendered GT) and values above max_disp in."""
+    torch.manual_seed(33)
+    d2 = torch.rand(shape) * 230.0 * (torch.rand(shape) > 0.25).float() * sign
+    r = F.interpolate(d2, scale_factor=0.5, mode="nearest", recompute_scale_factor=False)
+    ref = so.scatter_warp(r, r.type(torch.int))
+    ref_mask = (ref < 192) * (ref > 0)
+    from activezero_b200.utils import warp_ops as az_wo
+    out, mask = az_wo.disp_gt_from_right_view(d2.to(DEV), 192)
+    assert out.shape == ref.shape and mask.dtype == torch.bool
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(mask.cpu(), ref_mask)
+    # and against the unfused calls of this library
+    r_dev = F.interpolate(d2.to(DEV), scale_factor=0.5, mode="nearest", recompute_scale_factor=False)
+    assert torch.equal(out, ops.scatter_warp(r_dev, r_dev.type(torch.int)))
