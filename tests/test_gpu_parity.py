@@ -25,6 +25,12 @@ T = torch.from_numpy
 
 
 def close(a, b, rtol=1e-5, floor=1e-5):
+    """The gate of every "rtol 1e-5" row:  |a - b| <= rtol * |b| + floor * max|b|.
+    The second term is an ABSOLUTE floor relative to the tensor's largest magnitude: fp32 results carry ~6e-8 * max|b|
+    of rounding noise on every element, so a purely relative test would fail on elements that are ~0 by cancellation
+    (a gradient of 1e-9 next to gradients of 1) without saying anything about the kernel.  It is therefore a
+    "1e-5 of the tensor's scale" gate for small elements and a true relative 1e-5 gate for elements of typical size;
+    the failure message reports the worst error and the worst relative error so a regression shows which one moved."""
     a = a.detach().cpu().double()
     b = b.detach().cpu().double() if isinstance(b, torch.Tensor) else torch.as_tensor(b).double()
     atol = floor * float(b.abs().max()) + 1e-30 if b.numel() else 0.0  # 1e-30: fp32 underflows where fp64 holds 1e-100

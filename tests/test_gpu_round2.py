@@ -20,6 +20,7 @@ DEV = "cuda:0"
 
 
 def close(a, b, rtol=1e-5, floor=1e-5):
+    """|a - b| <= rtol * |b| + floor * max|b| (see tests/test_gpu_parity.py::close for why the floor is there)."""
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
     atol = floor * float(b.abs().max()) + 1e-30
     err = (a - b).abs()
