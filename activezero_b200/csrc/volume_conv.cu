@@ -195,6 +195,10 @@ __global__ void __launch_bounds__(256) volume_conv0_pack_kernel(const float* __r
     }
 }
 
+// volume_conv_v2.cu: shifted-coordinate, feature-stationary form (default when Dq <= 55)
+int volume_conv0_v2_launch(const float* L, const float* R, const float* wpacked, const float* scale, const float* shift,
+                           float* out, int B, int H, int W, int Dq, int relu, cudaStream_t st, bool* done);
+
 }  // namespace az
 
 using namespace az;
@@ -212,6 +216,13 @@ extern "C" int az_volume_conv0_fwd(const float* L, const float* R, const float* 
     if (!L || !R || !wpacked || !out || B <= 0 || H <= 0 || W <= 0 || Dq <= 0) return AZ_ERR_BAD_ARG;
     if (C != kVcC || (scale == nullptr) != (shift == nullptr)) return AZ_ERR_BAD_ARG;  // PSMNet: 32 + 32 -> 32 channels
     if (H > 65535 || Dq * B > 65535 || H * W >= (1ll << 31) || !aligned16(wpacked)) return AZ_ERR_BAD_ARG;
+    if (tuning("AZ_VCONV", 2) == 2) {
+        bool done = false;
+        const int rc = volume_conv0_v2_launch(L, R, wpacked, scale, shift, out, (int)B, (int)H, (int)W, (int)Dq, relu,
+                                              (cudaStream_t)stream, &done);
+        if (rc != 0) return rc;
+        if (done) return 0;
+    }
     const size_t smem = 2 * (size_t)kVcStage;
     cudaError_t e = cudaFuncSetAttribute(volume_conv0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
