@@ -25,14 +25,15 @@
 //     unmasked tap at all and are the epilogue of zero.
 //
 // CTA = one (b, y, tile of 128 shifted columns), all Dq planes.  Warps 0-3 are the epilogue (one TMEM lane = one output
-// row each), warp 4 issues the MMAs; accumulators of 8 planes live in tensor memory (8 x 32 columns, full / empty
+// row each), warps 4-7 issue the MMAs (planes round-robin); accumulators of 8 planes live in tensor memory (8 x 32 columns, full / empty
 // mbarriers), Q_0..2 in 96 more.  TF32 operands (cvt.rna at staging), fp32 accumulation, epilogue = optional
 // scale / shift (eval-mode BatchNorm) and ReLU, NCDHW stores.
 #include "common.cuh"
 
 namespace az {
 
-constexpr int kV2Threads = 160;
+constexpr int kV2Threads = 256;            // warps 0-3: epilogue, warps 4-7: one MMA-issuing thread each
+constexpr int kV2Issuers = 4;
 constexpr int kV2M = 128, kV2N = 32, kV2C = 32;
 constexpr int kV2RP = 184;                 // staged left positions: 128 + (Dq - 1) + 2 <= 184  =>  Dq <= 55
 constexpr int kV2RQ = 136;                 // staged right positions: 128 + 2 + 2
@@ -247,10 +248,13 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
     __syncthreads();
 
     // ---- phase 3: per-plane left-half GEMM (warp 4) and epilogue (warps 0-3), 8 accumulator slots in tensor memory
-    if (warp == 4) {
+    if (warp >= 4) {
+        // Four issuing threads, planes round-robin: one thread needs ~15 instructions per MMA (descriptor assembly on
+        // the uniform datapath, elect, predicate) and cannot keep the tensor core busy alone (measured: 8 k cycles per
+        // plane against 3.5 k of tensor-core time); accumulators are per plane, so the issuers are independent.
         if (lane == 0) {
             const uint64_t da0 = v2_desc(sbase, kV2RP * 16, 128), db0 = v2_desc(wbase, 512, 128);
-            for (int d = 0; d < Dq; ++d) {
+            for (int d = warp - 4; d < Dq; d += kV2Issuers) {
                 const int s = d & (kV2Slots - 1);
                 if (d >= kV2Slots) mbar_wait(&empty[s], (uint32_t)(((d >> 3) - 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
