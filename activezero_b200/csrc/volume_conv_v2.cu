@@ -38,7 +38,8 @@ constexpr int kV2M = 128, kV2N = 32, kV2C = 32;
 constexpr int kV2RP = 184;                 // staged left positions: 128 + (Dq - 1) + 2 <= 184  =>  Dq <= 55
 constexpr int kV2RQ = 136;                 // staged right positions: 128 + 2 + 2
 constexpr int kV2MaxDq = 55;
-constexpr int kV2Slots = 8;                // accumulator slots in tensor memory
+constexpr int kV2MT = 126;                 // output columns per tile: 128 operand rows serve the three kx taps of 126
+constexpr int kV2Slots = 4;                // accumulator slots in tensor memory (96 columns each: the three kx blocks)
 constexpr int kV2CacheBytes = 3 * 8 * kV2RP * 16;   // 70 656
 constexpr int kV2WBytes = 27 * 4096;                // 110 592: one half (32 channels) of every tap
 constexpr int kV2ClFloats = kV2MaxDq * 4 * 32, kV2CrFloats = kV2MaxDq * 32;
@@ -50,20 +51,39 @@ __device__ __forceinline__ uint64_t v2_desc(uint32_t saddr, uint32_t lbo_bytes, 
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-// c_format F32, a/b TF32, both K-major, N = 32, M = 128 (as volume_conv.cu)
+// c_format F32, a/b TF32, both K-major, M = 128; N = 32 (right-half terms) or 96 (left half: the three kx taps of a
+// (kd, ky) side by side -- in the no-swizzle layout tap kx is the same operand rows one row further, so the accumulator
+// block kx of operand row u belongs to output row u - kx and the three blocks are summed with a row shift in the
+// epilogue: the A operand is read once per 48 cycles of tensor-core math instead of once per 16)
 constexpr uint32_t kV2Idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kV2N >> 3) << 17) | ((uint32_t)(kV2M >> 4) << 24);
+constexpr uint32_t kV2Idesc96 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(kV2M >> 4) << 24);
 
 __device__ __forceinline__ float v2_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
-__device__ __forceinline__ void v2_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void v2_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc = kV2Idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(kV2Idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
         : "memory");
+}
+// wait with back-off: the issuing threads share their SM sub-partitions with the epilogue warps, and a tight try_wait
+// loop (it returns at once when the phase is not complete) took half of their issue slots (60 M spins per launch)
+__device__ __forceinline__ void v2_wait_sleep(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(128);
+    }
 }
 __device__ __forceinline__ void v2_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -91,12 +111,13 @@ __device__ __forceinline__ int v2_widx(int n, int c) {
 
 // sum_c w[c][n] * a[c] over the 32 channels of one half-tap block: both operands are 16-byte quads over c % 4
 // (weights: [j = c/8][kc][ng][r][e], staged rows: [chunk c/4][row][4]); `chunk_stride` floats between chunks of `a`
+template <int KC_STRIDE, int J_STRIDE>
 __device__ __forceinline__ float v2_dot32(const float* __restrict__ wt, int n, const float* __restrict__ a, int chunk_stride) {
     const float* wn = wt + 4 * (n & 7) + 32 * (n >> 3);
     float acc = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const float4 w4 = *reinterpret_cast<const float4*>(wn + 128 * (q & 1) + 256 * (q >> 1));
+        const float4 w4 = *reinterpret_cast<const float4*>(wn + KC_STRIDE * (q & 1) + J_STRIDE * (q >> 1));
         const float4 a4 = *reinterpret_cast<const float4*>(a + (size_t)q * chunk_stride);
         acc = fmaf(w4.x, a4.x, acc);
         acc = fmaf(w4.y, a4.y, acc);
@@ -125,6 +146,16 @@ __device__ __forceinline__ void v2_stage_rows(float* __restrict__ cache, const f
         reinterpret_cast<float4*>(cache)[(size_t)(ky * 8 + kq) * nrows + r] = v;
     }
 }
+// the left half of all 27 packed taps in the N = 96 operand order: [kd*3+ky][j][kc][kx][ng][r][e] (12 KB per (kd, ky))
+__device__ __forceinline__ void v2_stage_weights96(float* __restrict__ ws, const float* __restrict__ wpacked) {
+    for (int it = threadIdx.x; it < 27 * 256; it += kV2Threads) {
+        const int tap = it >> 8, q = it & 255;        // q = float4 index inside the tap's half: [j][kc][ng][r]
+        const int kdky = tap / 3, kx = tap - 3 * kdky;
+        const int j = q >> 6, kc = (q >> 5) & 1, ngr = q & 31;
+        reinterpret_cast<float4*>(ws)[kdky * 768 + j * 192 + kc * 96 + kx * 32 + ngr] =
+            __ldg(reinterpret_cast<const float4*>(wpacked + (size_t)tap * 2048) + q);
+    }
+}
 // one half (32 channels) of all 27 packed taps -> shared memory (4 KB per tap)
 __device__ __forceinline__ void v2_stage_weights(float* __restrict__ ws, const float* __restrict__ wpacked, int half) {
     for (int it = threadIdx.x; it < 27 * 256; it += kV2Threads) {
@@ -137,16 +168,17 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
                                                                        const float* __restrict__ wpacked,
                                                                        const float* __restrict__ scale,
                                                                        const float* __restrict__ shift, float* __restrict__ out,
-                                                                       int B, int H, int W, int Dq, int relu) {
+                                                                       int B, int H, int W, int Dq, int relu, int dbg) {
     extern __shared__ __align__(128) unsigned char vsm[];
     __shared__ __align__(8) uint64_t bar_q, full[kV2Slots], empty[kV2Slots];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float xch[2][4][3][32];  // kx = 1 / 2 blocks of a warp's first two rows, for the previous warp's last rows
     float* cache = reinterpret_cast<float*>(vsm);
     float* ws = reinterpret_cast<float*>(vsm + kV2CacheBytes);
     float* Cl = reinterpret_cast<float*>(vsm + kV2CacheBytes + kV2WBytes);  // [Dq][4][32]
     float* Cr = Cl + kV2ClFloats;                                          // [Dq][32]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int xt0 = -2 + kV2M * (int)blockIdx.x;  // first shifted column of the tile
+    const int xt0 = -2 + kV2MT * (int)blockIdx.x;  // first shifted column of the tile
     const int y = blockIdx.y, b = blockIdx.z;
     const size_t HW = (size_t)H * W;
     const uint32_t sbase = smem_u32(vsm), wbase = sbase + kV2CacheBytes;
@@ -198,7 +230,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
         const int d = o >> 5, n = o & 31;
         const int mstar = W - 1 - d - xt0;  // the tile row of output column W - 1 at plane d
         float acc = 0.f;
-        if (mstar >= 0 && mstar < kV2M) {
+        if (mstar >= 0 && mstar < kV2MT) {
             for (int kd = 0; kd < 3; ++kd) {
                 const int dp = d + kd - 1;
                 if (dp < 1 || dp >= Dq) continue;
@@ -206,7 +238,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
                 for (int ky = 0; ky < 3; ++ky) {
                     const int yp = y + ky - 1;
                     if (yp < 0 || yp >= H) continue;
-                    acc += v2_dot32(ws + ((kd * 3 + ky) * 3 + 2) * 1024, n, cache + ((size_t)(ky * 8) * kV2RQ + row) * 4, kV2RQ * 4);
+                    acc += v2_dot32<128, 256>(ws + ((kd * 3 + ky) * 3 + 2) * 1024, n, cache + ((size_t)(ky * 8) * kV2RQ + row) * 4, kV2RQ * 4);
                 }
             }
         }
@@ -217,7 +249,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
     __syncthreads();
     // ---- phase 2: left half operands.  Operand row of (m, d, kx) = m + d + kx  <->  column xt0 - 1 + row = x + kx - 1
     v2_stage_rows(cache, L, b, y, H, W, xt0 - 1, kV2RP);
-    v2_stage_weights(ws, wpacked, 0);
+    v2_stage_weights96(ws, wpacked);
     fence_async_smem();
     __syncthreads();
     // left-mask table for the rows xt = -2 .. 1 of the first tile (mask xt + kx >= kd):
@@ -238,7 +270,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
                     for (int ky = 0; ky < 3; ++ky) {
                         const int yp = y + ky - 1;
                         if (yp < 0 || yp >= H) continue;
-                        acc += v2_dot32(ws + ((kd * 3 + ky) * 3 + kx) * 1024, n, cache + ((size_t)(ky * 8) * kV2RP + row) * 4, kV2RP * 4);
+                        acc += v2_dot32<384, 768>(ws + (kd * 3 + ky) * 3072 + kx * 128, n, cache + ((size_t)(ky * 8) * kV2RP + row) * 4, kV2RP * 4);
                     }
                 }
             }
@@ -253,31 +285,28 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
         // the uniform datapath, elect, predicate) and cannot keep the tensor core busy alone (measured: 8 k cycles per
         // plane against 3.5 k of tensor-core time); accumulators are per plane, so the issuers are independent.
         if (lane == 0) {
-            const uint64_t da0 = v2_desc(sbase, kV2RP * 16, 128), db0 = v2_desc(wbase, 512, 128);
+            const uint64_t da0 = v2_desc(sbase, kV2RP * 16, 128), db0 = v2_desc(wbase, 1536, 128);
             for (int d = warp - 4; d < Dq; d += kV2Issuers) {
                 const int s = d & (kV2Slots - 1);
-                if (d >= kV2Slots) mbar_wait(&empty[s], (uint32_t)(((d >> 3) - 1) & 1));
+                if (d >= kV2Slots) v2_wait_sleep(&empty[s], (uint32_t)(((d >> 2) - 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t dst = tmem + 96 + 32 * s;
+                const uint32_t dst = tmem + 96 + 96 * s;
                 uint32_t acc = 0;
                 // descriptors differ from a base only in their start-address field (units of 16 bytes, no carry out
-                // of the field: shared memory is < 256 KB): one 64-bit add per operand per MMA -- the issuing thread
-                // must stay ahead of the tensor core (108 instructions per 3.5 k cycles)
+                // of the field: shared memory is < 256 KB): one 64-bit add per operand per MMA
                 for (int kd = 0; kd < 3; ++kd) {
                     const int dp = d + kd - 1;
                     if (dp < 0 || dp >= Dq) continue;
                     for (int ky = 0; ky < 3; ++ky) {
                         const int yp = y + ky - 1;
                         if (yp < 0 || yp >= H) continue;
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const uint64_t boff = (uint64_t)((((kd * 3 + ky) * 3 + kx) * 4096) >> 4);
+                        const uint64_t boff = (uint64_t)(((kd * 3 + ky) * 12288) >> 4);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint64_t da = da0 + (uint64_t)((ky * 8 + 2 * j) * kV2RP + d + kx);
-                                const uint64_t db = db0 + boff + (uint64_t)(j * 64);
-                                v2_mma(dst, da, db, acc);
-                                acc = 1;
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            const uint64_t da = da0 + (uint64_t)((ky * 8 + 2 * j) * kV2RP + d);
+                            const uint64_t db = db0 + boff + (uint64_t)(j * 192);
+                            v2_mma(dst, da, db, acc, kV2Idesc96);
+                            acc = 1;
                         }
                     }
                 }
@@ -304,13 +333,50 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
         const size_t cstride = (size_t)Dq * HW;
         for (int d = 0; d < Dq; ++d) {
             const int s = d & (kV2Slots - 1);
-            mbar_wait(&full[s], (uint32_t)((d >> 3) & 1));
+            mbar_wait(&full[s], (uint32_t)((d >> 2) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t v[32];
-            v2_ld32(lane_base + 96 + 32 * s, v);
+            uint32_t v[32], v1[32], v2[32];
+            v2_ld32(lane_base + 96 + 96 * s, v);        // block kx = 0: this row's own
+            v2_ld32(lane_base + 96 + 96 * s + 32, v1);  // block kx = 1: belongs to the row above (m - 1)
+            v2_ld32(lane_base + 96 + 96 * s + 64, v2);  // block kx = 2: belongs to row m - 2
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) v2_arrive(&empty[s]);  // the slot is free as soon as it is in registers
+            // out[m] = kx0[m] + kx1[m + 1] + kx2[m + 2]: shuffles inside the warp, the first two rows of the next warp
+            // through shared memory (double-buffered by plane parity; one named barrier of the four epilogue warps)
+            float (*xb)[3][32] = xch[d & 1];
+            if (dbg & 1) goto skip_combine;
+            if (!(dbg & 8) && lane < 2 && warp > 0) {
+#pragma unroll
+                for (int n = 0; n < 32; ++n) {
+                    if (lane == 0) xb[warp][0][n] = __uint_as_float(v1[n]);
+                    xb[warp][1 + lane][n] = __uint_as_float(v2[n]);
+                }
+            }
+            if (!(dbg & 4)) asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (!(dbg & 16)) {
+                // branch-free: every lane reads the (broadcast) hand-over values and selects -- a divergent branch per
+                // element for the last two lanes cost more than the whole GEMM (measured: 0.69 of 1.2 ms)
+                const int wn = warp < 3 ? warp + 1 : 3;  // warp 3's last rows (126, 127) are not outputs
+                const uint32_t x1 = smem_u32(xb[wn][0]), x2 = smem_u32(xb[wn][lane == 31 ? 2 : 1]);
+                const bool t1 = lane == 31, t2 = lane >= 30;
+#pragma unroll
+                for (int n = 0; n < 32; ++n) {
+                    // raw shfl.sync: around __shfl_down_sync the compiler emitted a WARPSYNC + BSSY / BSYNC / BRA guard per
+                    // element here (it cannot prove convergence behind the mbarrier spin loops): 6 x the instructions
+                    uint32_t u1, u2;
+                    asm volatile("shfl.sync.down.b32 %0, %1, 1, 0x1f, 0xffffffff;" : "=r"(u1) : "r"(v1[n]));
+                    asm volatile("shfl.sync.down.b32 %0, %1, 2, 0x1f, 0xffffffff;" : "=r"(u2) : "r"(v2[n]));
+                    // unconditional (volatile) loads + selects: a plain `t1 ? x1[n] : s1` became a branch around the load
+                    // plus a WARPSYNC before the next shuffle, per element
+                    float l1, l2;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l1) : "r"(x1 + 4 * n));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l2) : "r"(x2 + 4 * n));
+                    const float a1 = t1 ? l1 : __uint_as_float(u1), a2 = t2 ? l2 : __uint_as_float(u2);
+                    v[n] = __float_as_uint(__uint_as_float(v[n]) + a1 + a2);
+                }
+            }
+        skip_combine:
             const int x = xt0 + m + d;
             const bool first = blockIdx.x == 0;
             // left-mask rows of the first tile: replace (xt = -2, -1) or correct (xt = 0, 1) the accumulator
@@ -334,7 +400,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
                 }
             }
             float* o = out + ((size_t)b * kV2N * Dq + d) * HW + (size_t)y * W;
-            if (x >= 0 && x < W) {
+            if (!(dbg & 2) && m < kV2MT && x >= 0 && x < W) {
                 const float* cr = Cr + (size_t)d * 32;
 #pragma unroll
                 for (int n = 0; n < 32; ++n) {
@@ -369,8 +435,8 @@ int volume_conv0_v2_launch(const float* L, const float* R, const float* wpacked,
     cudaError_t e = cudaFuncSetAttribute(volume_conv0_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2Smem);
     if (e != cudaSuccess) return (int)e;
     // shifted columns -2 .. W - 1 (plane 0) must be covered
-    dim3 grid((unsigned)ceil_div(W + 2, kV2M), (unsigned)H, (unsigned)B);
-    volume_conv0_v2_kernel<<<grid, kV2Threads, kV2Smem, st>>>(L, R, wpacked, scale, shift, out, B, H, W, Dq, relu);
+    dim3 grid((unsigned)ceil_div(W + 2, kV2MT), (unsigned)H, (unsigned)B);
+    volume_conv0_v2_kernel<<<grid, kV2Threads, kV2Smem, st>>>(L, R, wpacked, scale, shift, out, B, H, W, Dq, relu, tuning("AZ_VCONV_DBG", 0));
     *done = true;
     return (int)cudaGetLastError();
 }
