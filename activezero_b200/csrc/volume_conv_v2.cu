@@ -32,7 +32,7 @@
 
 namespace az {
 
-constexpr int kV2Threads = 256;            // warps 0-3: epilogue, warps 4-7: one MMA-issuing thread each
+constexpr int kV2Threads = 384;            // warps 0-3 / 4-7: epilogue of the even / odd planes, warps 8-11: one MMA-issuing thread each
 constexpr int kV2Issuers = 4;
 constexpr int kV2M = 128, kV2N = 32, kV2C = 32;
 constexpr int kV2RP = 184;                 // staged left positions: 128 + (Dq - 1) + 2 <= 184  =>  Dq <= 55
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
     extern __shared__ __align__(128) unsigned char vsm[];
     __shared__ __align__(8) uint64_t bar_q, full[kV2Slots], empty[kV2Slots];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float xch[2][4][3][32];  // kx = 1 / 2 blocks of a warp's first two rows, for the previous warp's last rows
+    __shared__ float xch[2][2][4][3][32];  // [group][plane parity within the group][warp][block][n]  // kx = 1 / 2 blocks of a warp's first two rows, for the previous warp's last rows
     float* cache = reinterpret_cast<float*>(vsm);
     float* ws = reinterpret_cast<float*>(vsm + kV2CacheBytes);
     float* Cl = reinterpret_cast<float*>(vsm + kV2CacheBytes + kV2WBytes);  // [Dq][4][32]
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
-    if (tid == 4 * 32) {
+    if (tid == 8 * 32) {
         for (int kd = 0; kd < 3; ++kd) {
             uint32_t acc = 0;
             for (int ky = 0; ky < 3; ++ky) {
@@ -280,13 +280,13 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
     __syncthreads();
 
     // ---- phase 3: per-plane left-half GEMM (warp 4) and epilogue (warps 0-3), 8 accumulator slots in tensor memory
-    if (warp >= 4) {
+    if (warp >= 8) {
         // Four issuing threads, planes round-robin: one thread needs ~15 instructions per MMA (descriptor assembly on
         // the uniform datapath, elect, predicate) and cannot keep the tensor core busy alone (measured: 8 k cycles per
         // plane against 3.5 k of tensor-core time); accumulators are per plane, so the issuers are independent.
         if (lane == 0) {
             const uint64_t da0 = v2_desc(sbase, kV2RP * 16, 128), db0 = v2_desc(wbase, 1536, 128);
-            for (int d = warp - 4; d < Dq; d += kV2Issuers) {
+            for (int d = warp - 8; d < Dq; d += kV2Issuers) {
                 const int s = d & (kV2Slots - 1);
                 if (d >= kV2Slots) v2_wait_sleep(&empty[s], (uint32_t)(((d >> 2) - 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -314,8 +314,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
             }
         }
     } else {
-        const int m = tid;                      // tile row = TMEM lane
-        const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
+        const int grp = warp >> 2, wq = warp & 3;  // a warp reads the TMEM lanes 32 * (warp % 4) .. + 31
+        const int m = tid & 127;                   // tile row = TMEM lane
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * wq) << 16);
         // Q_0 + Q_1 + Q_2 stays in registers; the first / last plane (no kd = 0 / kd = 2) re-read the missing term
         float qs[32];
         {
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
             for (int n = 0; n < 32; ++n) qs[n] += __uint_as_float(v[n]);
         }
         const size_t cstride = (size_t)Dq * HW;
-        for (int d = 0; d < Dq; ++d) {
+        for (int d = grp; d < Dq; d += 2) {
             const int s = d & (kV2Slots - 1);
             mbar_wait(&full[s], (uint32_t)((d >> 2) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -344,20 +345,23 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
             if (lane == 0) v2_arrive(&empty[s]);  // the slot is free as soon as it is in registers
             // out[m] = kx0[m] + kx1[m + 1] + kx2[m + 2]: shuffles inside the warp, the first two rows of the next warp
             // through shared memory (double-buffered by plane parity; one named barrier of the four epilogue warps)
-            float (*xb)[3][32] = xch[d & 1];
+            float (*xb)[3][32] = xch[grp][(d >> 1) & 1];
             if (dbg & 1) goto skip_combine;
-            if (!(dbg & 8) && lane < 2 && warp > 0) {
+            if (!(dbg & 8) && lane < 2 && wq > 0) {
 #pragma unroll
                 for (int n = 0; n < 32; ++n) {
-                    if (lane == 0) xb[warp][0][n] = __uint_as_float(v1[n]);
-                    xb[warp][1 + lane][n] = __uint_as_float(v2[n]);
+                    if (lane == 0) xb[wq][0][n] = __uint_as_float(v1[n]);
+                    xb[wq][1 + lane][n] = __uint_as_float(v2[n]);
                 }
             }
-            if (!(dbg & 4)) asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (!(dbg & 4)) {
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                else asm volatile("bar.sync 2, 128;" ::: "memory");
+            }
             if (!(dbg & 16)) {
                 // branch-free: every lane reads the (broadcast) hand-over values and selects -- a divergent branch per
                 // element for the last two lanes cost more than the whole GEMM (measured: 0.69 of 1.2 ms)
-                const int wn = warp < 3 ? warp + 1 : 3;  // warp 3's last rows (126, 127) are not outputs
+                const int wn = wq < 3 ? wq + 1 : 3;  // the last warp's last rows (126, 127) are not outputs
                 const uint32_t x1 = smem_u32(xb[wn][0]), x2 = smem_u32(xb[wn][lane == 31 ? 2 : 1]);
                 const bool t1 = lane == 31, t2 = lane >= 30;
 #pragma unroll
