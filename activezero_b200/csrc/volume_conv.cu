@@ -191,7 +191,14 @@ __global__ void __launch_bounds__(256) volume_conv0_pack_kernel(const float* __r
     for (int t = threadIdx.x; t < kVcN * kVcK; t += 256) {
         const int e = t & 3, r = (t >> 2) & 7, ng = (t >> 5) & 3, kc = (t >> 7) & 1, j = t >> 8;
         const int n = 8 * ng + r, k = 8 * j + 4 * kc + e;
-        wpacked[(size_t)tap * kVcN * kVcK + t] = to_tf32(__ldg(w + ((size_t)n * kVcK + k) * 27 + tap));
+        const float v = to_tf32(__ldg(w + ((size_t)n * kVcK + k) * 27 + tap));
+        wpacked[(size_t)tap * kVcN * kVcK + t] = v;
+        // second copy of the LEFT half (k < 32) in the N = 96 operand order of volume_conv_v2.cu, after the 27 tap
+        // blocks: [kd*3+ky][j][kc][kx][ng][r][e] -- 12 KB per (kd, ky), one bulk copy each
+        if (k < 32) {
+            const int kdky = tap / 3, kx = tap - 3 * kdky;
+            wpacked[(size_t)27 * kVcN * kVcK + (size_t)kdky * 3072 + j * 768 + kc * 384 + kx * 128 + ng * 32 + r * 4 + e] = v;
+        }
     }
 }
 

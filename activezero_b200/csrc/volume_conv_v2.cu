@@ -114,17 +114,17 @@ __device__ __forceinline__ int v2_widx(int n, int c) {
 template <int KC_STRIDE, int J_STRIDE>
 __device__ __forceinline__ float v2_dot32(const float* __restrict__ wt, int n, const float* __restrict__ a, int chunk_stride) {
     const float* wn = wt + 4 * (n & 7) + 32 * (n >> 3);
-    float acc = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four chains of 8 instead of one of 32 dependent FMAs
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const float4 w4 = *reinterpret_cast<const float4*>(wn + KC_STRIDE * (q & 1) + J_STRIDE * (q >> 1));
         const float4 a4 = *reinterpret_cast<const float4*>(a + (size_t)q * chunk_stride);
-        acc = fmaf(w4.x, a4.x, acc);
-        acc = fmaf(w4.y, a4.y, acc);
-        acc = fmaf(w4.z, a4.z, acc);
-        acc = fmaf(w4.w, a4.w, acc);
+        a0 = fmaf(w4.x, a4.x, a0);
+        a1 = fmaf(w4.y, a4.y, a1);
+        a2 = fmaf(w4.z, a4.z, a2);
+        a3 = fmaf(w4.w, a4.w, a3);
     }
-    return acc;
+    return (a0 + a1) + (a2 + a3);
 }
 
 // Stage three feature rows (y-1, y, y+1) of `src` in the operand layout: cache[ky][chunk kq][row][4 channels], row r
@@ -146,31 +146,25 @@ __device__ __forceinline__ void v2_stage_rows(float* __restrict__ cache, const f
         reinterpret_cast<float4*>(cache)[(size_t)(ky * 8 + kq) * nrows + r] = v;
     }
 }
-// the left half of all 27 packed taps in the N = 96 operand order: [kd*3+ky][j][kc][kx][ng][r][e] (12 KB per (kd, ky))
-__device__ __forceinline__ void v2_stage_weights96(float* __restrict__ ws, const float* __restrict__ wpacked) {
-    for (int it = threadIdx.x; it < 27 * 256; it += kV2Threads) {
-        const int tap = it >> 8, q = it & 255;        // q = float4 index inside the tap's half: [j][kc][ng][r]
-        const int kdky = tap / 3, kx = tap - 3 * kdky;
-        const int j = q >> 6, kc = (q >> 5) & 1, ngr = q & 31;
-        reinterpret_cast<float4*>(ws)[kdky * 768 + j * 192 + kc * 96 + kx * 32 + ngr] =
-            __ldg(reinterpret_cast<const float4*>(wpacked + (size_t)tap * 2048) + q);
-    }
+// Weights reach shared memory by bulk async copies (TMA) issued by one thread while the other threads stage the
+// feature rows: the right half of the 27 tap blocks (4 KB each, tap-major) for phase 1, the left half in its N = 96
+// order (second part of the packed buffer, 12 KB per (kd, ky)) for phase 3.
+__device__ __forceinline__ void v2_copy_weights_right(float* ws, const float* __restrict__ wpacked, uint64_t* bar) {
+    mbar_expect_tx(bar, 27u * 4096u);
+    for (int tap = 0; tap < 27; ++tap) bulk_g2s(ws + tap * 1024, wpacked + (size_t)tap * 2048 + 1024, 4096u, bar);
 }
-// one half (32 channels) of all 27 packed taps -> shared memory (4 KB per tap)
-__device__ __forceinline__ void v2_stage_weights(float* __restrict__ ws, const float* __restrict__ wpacked, int half) {
-    for (int it = threadIdx.x; it < 27 * 256; it += kV2Threads) {
-        const int tap = it >> 8, q = it & 255;
-        reinterpret_cast<float4*>(ws)[it] = __ldg(reinterpret_cast<const float4*>(wpacked + (size_t)tap * 2048 + half * 1024) + q);
-    }
+__device__ __forceinline__ void v2_copy_weights_left96(float* ws, const float* __restrict__ wpacked, uint64_t* bar) {
+    mbar_expect_tx(bar, 9u * 12288u);
+    for (int k = 0; k < 9; ++k) bulk_g2s(ws + k * 3072, wpacked + (size_t)27 * 2048 + (size_t)k * 3072, 12288u, bar);
 }
 
 __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const float* __restrict__ L, const float* __restrict__ R,
                                                                        const float* __restrict__ wpacked,
                                                                        const float* __restrict__ scale,
                                                                        const float* __restrict__ shift, float* __restrict__ out,
-                                                                       int B, int H, int W, int Dq, int relu, int dbg) {
+                                                                       int B, int H, int W, int Dq, int relu) {
     extern __shared__ __align__(128) unsigned char vsm[];
-    __shared__ __align__(8) uint64_t bar_q, full[kV2Slots], empty[kV2Slots];
+    __shared__ __align__(8) uint64_t bar_q, bar_w, full[kV2Slots], empty[kV2Slots];
     __shared__ uint32_t tmem_base_s;
     __shared__ float xch[2][2][4][3][32];  // [group][plane parity within the group][warp][block][n]  // kx = 1 / 2 blocks of a warp's first two rows, for the previous warp's last rows
     float* cache = reinterpret_cast<float*>(vsm);
@@ -185,11 +179,13 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
 
     if (tid == 0) {
         mbar_init(&bar_q, 1);
+        mbar_init(&bar_w, 1);
         for (int s = 0; s < kV2Slots; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 4);
         }
         mbar_fence_init();
+        v2_copy_weights_right(ws, wpacked, &bar_w);  // overlaps the staging of the right rows
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
@@ -197,7 +193,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
     }
     // ---- phase 1: right half.  Q_kd[m][n] = sum_{ky, kx, c} Wr[kd,ky,kx][c][n] * R[c][y'][xt0 + m + kx - kd]
     v2_stage_rows(cache, R, b, y, H, W, xt0 - 2, kV2RQ);  // row r <-> column xt0 - 2 + r;  operand row = m + kx - kd + 2
-    v2_stage_weights(ws, wpacked, 1);
+    mbar_wait(&bar_w, 0);
     fence_async_smem();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -248,8 +244,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();
     // ---- phase 2: left half operands.  Operand row of (m, d, kx) = m + d + kx  <->  column xt0 - 1 + row = x + kx - 1
+    if (tid == 0) v2_copy_weights_left96(ws, wpacked, &bar_w);  // the right-half weights are dead (Q is complete)
     v2_stage_rows(cache, L, b, y, H, W, xt0 - 1, kV2RP);
-    v2_stage_weights96(ws, wpacked);
+    mbar_wait(&bar_w, 1);
     fence_async_smem();
     __syncthreads();
     // left-mask table for the rows xt = -2 .. 1 of the first tile (mask xt + kx >= kd):
@@ -346,19 +343,16 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
             // out[m] = kx0[m] + kx1[m + 1] + kx2[m + 2]: shuffles inside the warp, the first two rows of the next warp
             // through shared memory (double-buffered by plane parity; one named barrier of the four epilogue warps)
             float (*xb)[3][32] = xch[grp][(d >> 1) & 1];
-            if (dbg & 1) goto skip_combine;
-            if (!(dbg & 8) && lane < 2 && wq > 0) {
+            if (lane < 2 && wq > 0) {
 #pragma unroll
                 for (int n = 0; n < 32; ++n) {
                     if (lane == 0) xb[wq][0][n] = __uint_as_float(v1[n]);
                     xb[wq][1 + lane][n] = __uint_as_float(v2[n]);
                 }
             }
-            if (!(dbg & 4)) {
-                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-                else asm volatile("bar.sync 2, 128;" ::: "memory");
-            }
-            if (!(dbg & 16)) {
+            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            {
                 // branch-free: every lane reads the (broadcast) hand-over values and selects -- a divergent branch per
                 // element for the last two lanes cost more than the whole GEMM (measured: 0.69 of 1.2 ms)
                 const int wn = wq < 3 ? wq + 1 : 3;  // the last warp's last rows (126, 127) are not outputs
@@ -380,7 +374,6 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
                     v[n] = __float_as_uint(__uint_as_float(v[n]) + a1 + a2);
                 }
             }
-        skip_combine:
             const int x = xt0 + m + d;
             const bool first = blockIdx.x == 0;
             // left-mask rows of the first tile: replace (xt = -2, -1) or correct (xt = 0, 1) the accumulator
@@ -404,7 +397,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
                 }
             }
             float* o = out + ((size_t)b * kV2N * Dq + d) * HW + (size_t)y * W;
-            if (!(dbg & 2) && m < kV2MT && x >= 0 && x < W) {
+            if (m < kV2MT && x >= 0 && x < W) {
                 const float* cr = Cr + (size_t)d * 32;
 #pragma unroll
                 for (int n = 0; n < 32; ++n) {
@@ -440,7 +433,7 @@ int volume_conv0_v2_launch(const float* L, const float* R, const float* wpacked,
     if (e != cudaSuccess) return (int)e;
     // shifted columns -2 .. W - 1 (plane 0) must be covered
     dim3 grid((unsigned)ceil_div(W + 2, kV2MT), (unsigned)H, (unsigned)B);
-    volume_conv0_v2_kernel<<<grid, kV2Threads, kV2Smem, st>>>(L, R, wpacked, scale, shift, out, B, H, W, Dq, relu, tuning("AZ_VCONV_DBG", 0));
+    volume_conv0_v2_kernel<<<grid, kV2Threads, kV2Smem, st>>>(L, R, wpacked, scale, shift, out, B, H, W, Dq, relu);
     *done = true;
     return (int)cudaGetLastError();
 }

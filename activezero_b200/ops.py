@@ -141,7 +141,7 @@ def pack_volume_conv_weight(weight: torch.Tensor) -> torch.Tensor:
     w = _cuda_f32(weight.detach(), "weight")
     if tuple(w.shape) != (32, 64, 3, 3, 3):
         raise ValueError(f"volume conv: expected a [32,64,3,3,3] Conv3d weight, got {tuple(w.shape)}")
-    packed = torch.empty((27, 32 * 64), dtype=torch.float32, device=w.device)
+    packed = torch.empty((27 * 3072,), dtype=torch.float32, device=w.device)  # AZ_VOLUME_CONV0_PACKED_FLOATS
     with torch.cuda.device(w.device):
         _lib.call("az_volume_conv0_pack", _ptr(w), _ptr(packed), _stream())
     return packed
@@ -155,7 +155,7 @@ def volume_conv0(ref_feat, tgt_feat, wpacked, num_disp: int, scale=None, shift=N
     if C != 32:
         raise ValueError("volume conv: PSMNet's 32 feature channels expected")
     wp = _cuda_f32(wpacked, "wpacked")
-    if wp.numel() != 27 * 32 * 64 or wp.device != L.device:
+    if wp.numel() != 27 * 3072 or wp.device != L.device:
         raise ValueError("volume conv: wpacked must come from pack_volume_conv_weight on the features' device")
     if (scale is None) != (shift is None):
         raise ValueError("volume conv: scale and shift go together")

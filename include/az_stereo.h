@@ -56,9 +56,10 @@ int az_concat_volume_bwd_ndhwc(const float* gvol, float* gL, float* gR,
  *      implicit -- nets/psmnet/psmnet.py:151-168 (volume + dres0[0] = Conv3d(64,32,3,1,1,bias=False)), psmnet_submodule.py:44-56.
  * out[b,co,d,y,x] = sum_{ci,kd,ky,kx} weight[co,ci,kd,ky,kx] * vol[b,ci,d+kd-1,y+ky-1,x+kx-1] (zero padding) with vol
  * the concat volume of az_concat_volume_fwd, never materialised: tcgen05 TF32 implicit GEMM, fp32 accumulation in
- * tensor memory.  L,R: [B,32,H,W]; out: [B,32,Dq,H,W]; wpacked: 27*32*64 floats produced ONCE per weight tensor by
+ * tensor memory.  L,R: [B,32,H,W]; out: [B,32,Dq,H,W]; wpacked: AZ_VOLUME_CONV0_PACKED_FLOATS (= 27*3072) floats produced ONCE per weight tensor by
  * az_volume_conv0_pack from the Conv3d weight [32,64,3,3,3]; scale/shift: float[32] or both NULL (an eval-mode
  * BatchNorm folded into the epilogue: out*scale+shift), relu != 0 applies max(.,0) last. */
+#define AZ_VOLUME_CONV0_PACKED_FLOATS (27 * 3072)
 int az_volume_conv0_pack(const float* weight, float* wpacked, void* stream);
 int az_volume_conv0_fwd(const float* L, const float* R, const float* wpacked, const float* scale, const float* shift,
                         float* out, int64_t B, int64_t C, int64_t H, int64_t W, int64_t Dq, int relu, void* stream);
