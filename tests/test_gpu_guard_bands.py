@@ -204,3 +204,21 @@ def test_patch_loss_and_warp_writes_stay_inside(shape, ps):
     out.check("warped")
     gimg.check("warp gimg")
     gdisp.check("warp gdisp")
+
+
+@pytest.mark.parametrize("shape,dq", [((1, 32, 3, 130), 7), ((2, 32, 2, 37), 48), ((1, 32, 5, 254), 3), ((1, 32, 2, 60), 56)])
+def test_volume_conv0_writes_stay_inside(shape, dq):
+    """Both tcgen05 kernels (dq = 56 takes the first form): output and packed-weight buffers between canaries."""
+    torch.manual_seed(49)
+    B, C, H, W = shape
+    L, R = torch.randn(shape, device=DEV), torch.randn(shape, device=DEV)
+    w = torch.randn(32, 64, 3, 3, 3, device=DEV) * 0.05
+    wp = Guarded((27 * 3072,), torch.float32)
+    _lib.call("az_volume_conv0_pack", _ptr(w), _ptr(wp.t), _stream())
+    out = Guarded((B, 32, dq, H, W), torch.float32)
+    _lib.call("az_volume_conv0_fwd", _ptr(L), _ptr(R), _ptr(wp.t), ctypes.c_void_p(0), ctypes.c_void_p(0), _ptr(out.t), B, C, H, W, dq, 0,
+              _stream())
+    torch.cuda.synchronize()
+    wp.check("packed weights")
+    out.check("conv output")
+    assert torch.equal(out.t, ops.volume_conv0(L, R, wp.t, dq))
