@@ -541,6 +541,44 @@ def run_b200(args, rank, world, local_rank):
             stock = time_stock_torch_gpu(L[:STOCK_B], R[:STOCK_B], cost[:STOCK_B], pat_L[:STOCK_B], pat_R[:STOCK_B],
                                          mask[:STOCK_B])
 
+        # ---- informational: SURVEY §8f-2, the first aggregation convolution (Conv3d 64 -> 32, 3x3x3 on the concat volume,
+        # psmnet.py:165-168) on the IMPLICIT volume -- the one tensor-core kernel of the library (tcgen05 TF32, TMEM) --
+        # against volume + cuDNN on the same 2 pairs.  Not part of value / e2e.
+        vconv = None
+        if world == 1 and not args.no_stock_variant:
+            import torch.nn.functional as F_
+
+            VB = 2
+            wconv = torch.randn(32, 64, 3, 3, 3, device=dev) * 0.05
+            wp = ops.pack_volume_conv_weight(wconv)
+            Lv, Rv = L[:VB].contiguous(), R[:VB].contiguous()
+
+            def _time(fn, n=10):
+                for _ in range(3):
+                    fn()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a_.record()
+                for _ in range(n):
+                    fn()
+                b_.record()
+                torch.cuda.synchronize()
+                return a_.elapsed_time(b_) / n
+
+            ms_v = _time(lambda: ops.volume_conv0(Lv, Rv, wp, DQ))
+            ms_lib = _time(lambda: F_.conv3d(ops.build_concat_volume(Lv, Rv, DQ, channels_last=True), wconv.contiguous(
+                memory_format=torch.channels_last_3d), padding=1))
+            flop_nominal = 2.0 * VB * DQ * HQ * WQ * 32 * 64 * 27
+            vconv = {"note": "informational: first aggregation convolution on the implicit volume (tcgen05 TF32, fp32 accumulation "
+                             "in tensor memory; the right half of the volume is shift-invariant in x - d and computed once per "
+                             "row, so about half of the nominal FLOPs are executed) vs this repo's channels_last_3d volume + "
+                             "cuDNN conv3d (TF32) on the same pairs",
+                     "pairs": VB, "ms": ms_v, "ms_volume_plus_cudnn": ms_lib, "speedup": ms_lib / ms_v,
+                     "roofline": {"bound": "tensor", "achieved": flop_nominal / (ms_v * 1e-3) / 1e12, "unit": "TFLOP/s (nominal FLOPs)",
+                                  "peak": 1125.0, "peak_source": "nominal dense TF32 = half of the 2.25 PFLOP/s bf16 figure",
+                                  "frac": flop_nominal / (ms_v * 1e-3) / 1e12 / 1125.0}}
+            del wconv, wp, Lv, Rv
+
     ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train, ms_h2d, ms_fused_k, ms_eager = dist_util.max_over_ranks(
         [ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train, ms_h2d, ms_fused_k, ms_eager], dev)
 
@@ -634,6 +672,8 @@ def run_b200(args, rank, world, local_rank):
         if stock is not None:
             stock["speedup_of_value_per_pair"] = (line["value"] / world) / stock["value"]
             line["variant_stock_torch_gpu"] = stock
+        if vconv is not None:
+            line["variant_implicit_volume_conv"] = vconv
         if world == 1 and not args.no_cpu_baseline:
             pairs_s, _, cores = time_cpu_reference(12, 1)  # ~10 s of CPU work on the box's host cores
             line["cpu_baseline"] = {"value": pairs_s, "unit": UNIT, "cores": cores, "kind": "port",
