@@ -32,8 +32,8 @@
 
 namespace az {
 
-constexpr int kV2Threads = 384;            // warps 0-3 / 4-7: epilogue of the even / odd planes, warps 8-11: one MMA-issuing thread each
-constexpr int kV2Issuers = 4;
+constexpr int kV2Issuers = 3;               // three issuing threads keep up with N = 96 (36 MMAs per plane)
+constexpr int kV2Threads = 256 + 32 * kV2Issuers;  // warps 0-3 / 4-7: epilogue of the even / odd planes, then the issuers
 constexpr int kV2M = 128, kV2N = 32, kV2C = 32;
 constexpr int kV2RP = 184;                 // staged left positions: 128 + (Dq - 1) + 2 <= 184  =>  Dq <= 55
 constexpr int kV2RQ = 136;                 // staged right positions: 128 + 2 + 2
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
     extern __shared__ __align__(128) unsigned char vsm[];
     __shared__ __align__(8) uint64_t bar_q, bar_w, full[kV2Slots], empty[kV2Slots];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float2 ss[32];              // eval-mode BatchNorm (scale, shift) per output channel, or (1, 0)
     __shared__ float xch[2][2][4][3][32];  // [group][plane parity within the group][warp][block][n]  // kx = 1 / 2 blocks of a warp's first two rows, for the previous warp's last rows
     float* cache = reinterpret_cast<float*>(vsm);
     float* ws = reinterpret_cast<float*>(vsm + kV2CacheBytes);
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
     const size_t HW = (size_t)H * W;
     const uint32_t sbase = smem_u32(vsm), wbase = sbase + kV2CacheBytes;
 
+    if (tid < 32) ss[tid] = scale != nullptr ? make_float2(__ldg(scale + tid), __ldg(shift + tid)) : make_float2(1.f, 0.f);
     if (tid == 0) {
         mbar_init(&bar_q, 1);
         mbar_init(&bar_w, 1);
@@ -399,11 +401,13 @@ __global__ void __launch_bounds__(kV2Threads, 1) volume_conv0_v2_kernel(const fl
             float* o = out + ((size_t)b * kV2N * Dq + d) * HW + (size_t)y * W;
             if (m < kV2MT && x >= 0 && x < W) {
                 const float* cr = Cr + (size_t)d * 32;
+                const bool xr = x == W - 1;  // one row per plane
 #pragma unroll
                 for (int n = 0; n < 32; ++n) {
-                    float val = __uint_as_float(v[n]) + qs[n];
-                    if (x == W - 1) val -= cr[n];
-                    if (scale != nullptr) val = fmaf(val, __ldg(scale + n), __ldg(shift + n));
+                    const float2 sc = ss[n];  // (scale, shift) or (1, 0): broadcast shared-memory read
+                    const float c = cr[n];    // unconditional read + select (a branch per element costs more)
+                    float val = __uint_as_float(v[n]) + qs[n] - (xr ? c : 0.f);
+                    val = fmaf(val, sc.x, sc.y);
                     if (relu) val = fmaxf(val, 0.f);
                     o[(size_t)n * cstride + x] = val;
                 }
