@@ -1,5 +1,5 @@
 """CPU: the one-JSON-line contract of bench.py.  The B200 arm cannot run here, so its committed output
-(profiles/r1_bench_v6.json, written by `python bench.py --steps 20 --warmup 5` on a B200) is checked for the keys
+(profiles/r2_bench_final.json, written by `python bench.py` on a B200) is checked for the keys
 and the internal consistency the driver relies on; the reference arm (CPU oracle) is executed for real."""
 import json
 import os
@@ -12,7 +12,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_committed_b200_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_v6.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_final.json")))
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
     assert d["metric"] in base["metric"] and d["unit"] == "pairs/s" and d["higher_is_better"] is True
@@ -38,6 +38,13 @@ def test_committed_b200_line_has_the_contract_keys():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference")
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+    # round 2: nominal-peak fractions, the non-HBM kernels on their own rooflines, the tensor-core variant
+    assert 0 < r["frac_nominal"] < r["frac"] and 0.7 < r["pipeline_frac"] < 1.0
+    patch = next(k for k in d["kernels"] if "patch" in k["kernel"])
+    assert patch["bound"].startswith("lsu") and 0 < patch["frac"] < 1
+    assert d["variant_fused_upsample"]["fused_soft_argmin_kernel"]["bound"] == "mufu"
+    vc = d["variant_implicit_volume_conv"]
+    assert vc["roofline"]["bound"] == "tensor" and 0 < vc["roofline"]["frac"] < 1 and vc["speedup"] > 1.0
 
 
 def test_reference_arm_runs_and_prints_one_json_line():
@@ -48,8 +55,8 @@ def test_reference_arm_runs_and_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and BASE_KEYS <= set(d)
-    ref = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_v6.json")))
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_final.json")))
     assert d["metric"] == ref["metric"] and d["unit"] == ref["unit"] and d["higher_is_better"] is True
-    assert d["config"]["workload"] == ref["config"]["workload"]
+    assert d["config"] == ref["config"]  # the driver compares the two arms' config dicts (`same_config`)
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
