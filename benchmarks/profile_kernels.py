@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Launch every kernel of libaz_stereo.so once (after one warm-up) at BASELINE config-2 per-pair
-sizes, for `ncu --set full` (profiles/README.md has the command).  No timing here."""
+"""Launch every kernel of libaz_stereo.so once (after one warm-up; `--iters 1` skips the warm-up pass) at BASELINE
+config-2 per-pair sizes, for `ncu --set full` (profiles/README.md has the command).  No timing here."""
 import os
 import sys
 
@@ -10,6 +10,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from activezero_b200 import ops  # noqa: E402
+from activezero_b200.utils import reprojection as rp  # noqa: E402
 
 DEV = "cuda:0"
 B, C, Hq, Wq, D, PS = 2, 32, 136, 240, 192, 11
@@ -28,7 +29,14 @@ def main():
     g1 = torch.randn(B, 1, H, W, device=DEV)
     di = (torch.rand(B, 1, H, W, device=DEV) * 64).int()
     frames = torch.randint(0, 255, (B, 7, H, W), dtype=torch.uint8, device=DEV)
-    for it in range(2):
+    d2x = torch.rand(B, 1, 2 * H, 2 * W, device=DEV) * 60  # the trainer's double-resolution right-view disparity
+    depth = torch.rand(B, 1, H, W, device=DEV) + 0.5
+    focal, base = torch.full((B,), 446.0, device=DEV), torch.full((B,), 0.055, device=DEV)
+    ir = torch.randint(0, 255, (B, H, W), dtype=torch.uint8, device=DEV)
+    no_ir = torch.randint(0, 255, (B, H, W), dtype=torch.uint8, device=DEV)
+    w0 = torch.randn(32, 64, 3, 3, 3, device=DEV) * 0.05
+    iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 2
+    for it in range(iters):
         vol = ops.build_concat_volume(L, R, Dq)
         vol.backward(torch.ones_like(vol))
         volc = ops.build_concat_volume(L, R, Dq, channels_last=True)  # channels_last_3d order, SURVEY 8f rank 2
@@ -52,6 +60,17 @@ def main():
         ops.scatter_warp(disp.detach(), di, check_sign=False)
         ops.temporal_ir_pattern(frames)
         ops.local_contrast_norm(pL, 9)
+        # round-2 entry points: image gradient of the warp, the GT chain, a9's rescaling + multi-scale loss,
+        # error metrics, simulated-IR pattern, the first aggregation convolution on the implicit volume
+        im = pR.clone().requires_grad_(True)
+        ops.warp(im, dd.detach()).backward(g1)
+        ops.scatter_warp_gt(d2x, 192.0, check_sign=False)
+        ms = rp.get_reprojection_error_diff_ratio(pL, pR, dd, mask)
+        (ms[0] if isinstance(ms, (tuple, list)) else ms).backward()
+        dd.grad = None
+        ops.error_metric_sums(disp.detach() + 1, depth, disp.detach(), mask, focal_length=focal, baseline=base)
+        ops.sim_ir_pattern(ir, no_ir)
+        ops.volume_conv0(L, R, ops.pack_volume_conv_weight(w0), Dq)
         for t in (L, R, cost, low):
             t.grad = None
         torch.cuda.synchronize()
