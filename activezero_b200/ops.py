@@ -179,8 +179,8 @@ class GwcVolumeFn(torch.autograd.Function):
     def forward(ctx, ref_feat, tgt_feat, num_disp: int, num_groups: int):
         L, R = check_feature_pair(ref_feat, tgt_feat, "gwc volume")
         B, C, H, W = L.shape
-        if C % int(num_groups) != 0:
-            raise ValueError("gwc volume: C must be divisible by num_groups")
+        if int(num_disp) <= 0 or int(num_groups) <= 0 or C % int(num_groups) != 0:
+            raise ValueError(f"gwc volume: num_disp > 0 and num_groups dividing C={C} expected")
         vol = torch.empty((B, int(num_groups), int(num_disp), H, W), dtype=torch.float32, device=L.device)
         with torch.cuda.device(L.device):
             _lib.call("az_gwc_volume_fwd", _ptr(L), _ptr(R), _ptr(vol), B, C, H, W, int(num_disp), int(num_groups),
@@ -306,8 +306,9 @@ class WarpFn(torch.autograd.Function):
     def forward(ctx, img, disp):
         im = _cuda_f32(img, "img")
         d = _cuda_f32(disp, "disp")
-        if im.dim() != 4 or d.dim() != 4 or d.shape[1] != 1 or d.shape[0] != im.shape[0] or d.shape[2:] != im.shape[2:]:
-            raise ValueError("apply_disparity: img [B,C,H,W], disp [B,1,H,W]")
+        if im.dim() != 4 or d.dim() != 4 or d.shape[1] != 1 or d.shape[0] != im.shape[0] or d.shape[2:] != im.shape[2:] \
+                or d.device != im.device:
+            raise ValueError("apply_disparity: img [B,C,H,W], disp [B,1,H,W] on one device expected")
         B, C, H, W = im.shape
         out = torch.empty_like(im)
         lx, ly = linspace_table(W, im.device), linspace_table(H, im.device)
@@ -484,6 +485,8 @@ def scatter_warp(img, disp, check_sign: bool = True):
     assert disp.dtype == torch.int
     if img.dtype != torch.float32:
         raise ValueError("apply_disparity_cu: img must be float32")
+    if img.dim() != 4 or img.device != disp.device:
+        raise ValueError("apply_disparity_cu: img [N,C,H,W] and disp on the same device expected")
     N, C, H, W = img.shape
     if disp.numel() != N * H * W:
         raise ValueError("apply_disparity_cu: disp must be [N,H,W] or [N,1,H,W]")
@@ -525,6 +528,8 @@ def temporal_ir_pattern(frames, ks: int = 11, threshold: float = 0.005):
         raise ValueError("temporal_ir_pattern: expected a CUDA uint8 tensor")
     squeeze = frames.dim() == 3
     f = (frames.unsqueeze(0) if squeeze else frames).contiguous()
+    if f.dim() != 4:
+        raise ValueError("temporal_ir_pattern: [T,H,W] or [B,T,H,W] expected")
     B, T, H, W = f.shape
     pat = torch.empty((B, H, W), dtype=torch.float32, device=f.device)
     ws = torch.empty((_lib.query("az_temporal_ir_workspace_bytes", B, H, W),), dtype=torch.uint8, device=f.device)
@@ -540,6 +545,8 @@ def local_contrast_norm(image, kernel_size: int = 9, eps: float = 1e-5):
         # the reference's LCN is ordinary autograd code; this kernel is forward-only (the trainer normalises data)
         raise ValueError("local_contrast_norm: the CUDA operator is not differentiable; detach the image first")
     im = _cuda_f32(image.detach(), "image")
+    if im.dim() != 4:
+        raise ValueError("local_contrast_norm: image must be [B,C,H,W]")
     B, Cin, H, W = im.shape
     normed = torch.empty((B, 1, H, W), dtype=torch.float32, device=im.device)
     std = torch.empty_like(normed)
@@ -555,8 +562,9 @@ def error_metric_sums(disp_gt, depth_gt, disp_pred, mask, depth_pred=None, focal
     dg = _cuda_f32(disp_gt.detach(), "disp_gt")
     zg = _cuda_f32(depth_gt.detach(), "depth_gt")
     dp = _cuda_f32(disp_pred.detach(), "disp_pred")
-    if dg.dim() != 4 or dg.shape[1] != 1 or zg.shape != dg.shape or dp.shape != dg.shape:
-        raise ValueError("error metrics: disp_gt, depth_gt, disp_pred must all be [B,1,H,W]")
+    if dg.dim() != 4 or dg.shape[1] != 1 or zg.shape != dg.shape or dp.shape != dg.shape \
+            or not (dg.device == zg.device == dp.device):
+        raise ValueError("error metrics: disp_gt, depth_gt, disp_pred must all be [B,1,H,W] on one device")
     B, _, H, W = dg.shape
     m = _mask_u8(mask, dg)
     zp = f = bl = None

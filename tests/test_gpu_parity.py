@@ -672,7 +672,7 @@ def test_ops_inside_autocast_compute_in_fp32():
         vol = ops.build_concat_volume(L, R, 4)
     assert out.dtype == torch.float32 and torch.equal(out, ref)
     assert half_in.dtype == torch.float32
-    assert float((half_in - ops.soft_argmin(cost.half().float())).abs().max()) == 0.0
+    assert float((half_in - ops.soft_argmin(cost.half().float())).detach().abs().max()) == 0.0
     assert vol.dtype == torch.float32 and torch.equal(vol, so.concat_volume(L.detach(), R, 4))
     (out.sum() + vol.sum()).backward()
     assert cost.grad is not None and L.grad is not None and cost.grad.dtype == torch.float32
