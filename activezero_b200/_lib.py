@@ -93,10 +93,14 @@ def load() -> ctypes.CDLL:
     return lib
 
 
-def call(name: str, *args):
-    """Invoke a compute entry point; raise on any non-zero status."""
+def call(name: str, *args, batch=None):
+    """Invoke a compute entry point; raise on any non-zero status.  ``batch=0`` (an empty batch: the reference's
+    torch code returns empty tensors there) enqueues nothing -- there is no element to compute and a zero-sized
+    grid is not launchable; the C ABI itself rejects non-positive sizes."""
     global launch_count, kernel_launches
     lib = load()
+    if batch is not None and int(batch) == 0:
+        return
     rc = getattr(lib, name)(*args)
     launch_count += 1
     kernel_launches += KERNELS_PER_CALL.get(name, 1)
@@ -106,4 +110,5 @@ def call(name: str, *args):
 
 
 def query(name: str, *args) -> int:
-    return int(getattr(load(), name)(*args))
+    """Workspace-size queries; never negative (an empty batch needs no workspace)."""
+    return max(0, int(getattr(load(), name)(*args)))

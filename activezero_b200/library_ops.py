@@ -50,7 +50,7 @@ def concat_volume(ref: Tensor, tgt: Tensor, num_disp: int, channels_last: bool) 
                       memory_format=torch.channels_last_3d if ndhwc else torch.contiguous_format)
     with torch.cuda.device(L.device):
         _lib.call("az_concat_volume_fwd_ndhwc" if ndhwc else "az_concat_volume_fwd", _ptr(L), _ptr(R), _ptr(vol),
-                  B, C, H, W, num_disp, _stream())
+                  B, C, H, W, num_disp, _stream(), batch=B)
     return vol.contiguous(memory_format=torch.channels_last_3d) if channels_last and not ndhwc else vol
 
 
@@ -72,7 +72,7 @@ def concat_volume_backward(gvol: Tensor, C: int) -> Tuple[Tensor, Tensor]:
     gR = torch.empty_like(gL)
     with torch.cuda.device(g.device):
         _lib.call("az_concat_volume_bwd_ndhwc" if ndhwc else "az_concat_volume_bwd", _ptr(g), _ptr(gL), _ptr(gR),
-                  B, C, H, W, Dq, _stream())
+                  B, C, H, W, Dq, _stream(), batch=B)
     return gL, gR
 
 
@@ -106,7 +106,7 @@ def soft_argmin_op(cost: Tensor) -> Tuple[Tensor, Tensor]:
     disp = torch.empty((B, 1, H, W), dtype=torch.float32, device=c.device)
     lse = torch.empty((B, 2, H, W), dtype=torch.float32, device=c.device)
     with torch.cuda.device(c.device):
-        _lib.call("az_soft_argmin_fwd", _ptr(c), _ptr(disp), _ptr(lse), B, D, H, W, _stream())
+        _lib.call("az_soft_argmin_fwd", _ptr(c), _ptr(disp), _ptr(lse), B, D, H, W, _stream(), batch=B)
     return disp, lse
 
 
@@ -129,7 +129,7 @@ def soft_argmin_backward(cost: Tensor, disp: Tensor, lse: Tensor, gdisp: Tensor)
     disp, lse = d_, l_
     gcost = torch.empty_like(c)
     with torch.cuda.device(c.device):
-        _lib.call("az_soft_argmin_bwd", _ptr(c), _ptr(disp), _ptr(lse), _ptr(g), _ptr(gcost), B, D, H, W, _stream())
+        _lib.call("az_soft_argmin_bwd", _ptr(c), _ptr(disp), _ptr(lse), _ptr(g), _ptr(gcost), B, D, H, W, _stream(), batch=B)
     return gcost
 
 
@@ -174,7 +174,10 @@ def reproj_loss_op(tgt: Tensor, src: Tensor, disp: Tensor, mask: Tensor, ps: int
     lx, ly = linspace_table(W, dev), linspace_table(H, dev)
     with torch.cuda.device(dev):
         _lib.call("az_reproj_loss_fwd", _ptr(t), _ptr(s), _ptr(d), float(sign), _ptr(m), _ptr(lx), _ptr(ly), int(ps),
-                  _ptr(warped), _ptr(gpre), _ptr(loss), _ptr(stats), _ptr(ws), B, C, H, W, _stream())
+                  _ptr(warped), _ptr(gpre), _ptr(loss), _ptr(stats), _ptr(ws), B, C, H, W, _stream(), batch=B)
+    if B == 0:  # F.mse_loss of nothing is NaN
+        loss.fill_(float("nan"))
+        stats.zero_()
     return loss.reshape(()), warped, gpre, stats
 
 
@@ -195,7 +198,7 @@ def reproj_loss_backward(gpre: Tensor, stats: Tensor, gloss: Tensor, sign: float
     gdisp = torch.empty_like(gpre)
     with torch.cuda.device(gpre.device):
         _lib.call("az_reproj_loss_bwd", _ptr(gpre), _ptr(stats), _ptr(gl), float(sign), _ptr(gdisp), B, C, H, W, int(ps),
-                  _stream())
+                  _stream(), batch=B)
     return gdisp
 
 
@@ -243,7 +246,7 @@ def gwc_volume(ref: Tensor, tgt: Tensor, num_disp: int, num_groups: int) -> Tens
     B, C, H, W = _gwc_dims(L, num_disp, num_groups, "az_stereo::gwc_volume")
     vol = torch.empty((B, num_groups, num_disp, H, W), dtype=torch.float32, device=L.device)
     with torch.cuda.device(L.device):
-        _lib.call("az_gwc_volume_fwd", _ptr(L), _ptr(R), _ptr(vol), B, C, H, W, num_disp, num_groups, _stream())
+        _lib.call("az_gwc_volume_fwd", _ptr(L), _ptr(R), _ptr(vol), B, C, H, W, num_disp, num_groups, _stream(), batch=B)
     return vol
 
 
@@ -263,7 +266,7 @@ def gwc_volume_backward(gvol: Tensor, ref: Tensor, tgt: Tensor) -> Tuple[Tensor,
     B, C, H, W = _gwc_dims(L, Dq, G, "az_stereo::gwc_volume_backward")
     gL, gR = torch.empty_like(L), torch.empty_like(R)
     with torch.cuda.device(L.device):
-        _lib.call("az_gwc_volume_bwd", _ptr(g), _ptr(L), _ptr(R), _ptr(gL), _ptr(gR), B, C, H, W, Dq, G, _stream())
+        _lib.call("az_gwc_volume_bwd", _ptr(g), _ptr(L), _ptr(R), _ptr(gL), _ptr(gR), B, C, H, W, Dq, G, _stream(), batch=B)
     return gL, gR
 
 
@@ -301,7 +304,7 @@ def upsample_soft_argmin_op(lowres: Tensor, D: int, H: int, W: int) -> Tuple[Ten
     disp = torch.empty((B, 1, H, W), dtype=torch.float32, device=c.device)
     stats = torch.empty((B, 2, H, W), dtype=torch.float32, device=c.device)
     with torch.cuda.device(c.device):
-        _lib.call("az_upsample_soft_argmin_fwd", _ptr(c), _ptr(disp), _ptr(stats), B, Dq, Hq, Wq, D, H, W, _stream())
+        _lib.call("az_upsample_soft_argmin_fwd", _ptr(c), _ptr(disp), _ptr(stats), B, Dq, Hq, Wq, D, H, W, _stream(), batch=B)
     return disp, stats
 
 
@@ -325,7 +328,7 @@ def upsample_soft_argmin_backward(lowres: Tensor, disp: Tensor, stats: Tensor, g
                      device=c.device)
     with torch.cuda.device(c.device):
         _lib.call("az_upsample_soft_argmin_bwd", _ptr(c), _ptr(d_), _ptr(s_), _ptr(g), _ptr(glow), _ptr(ws),
-                  B, Dq, Hq, Wq, D, H, W, _stream())
+                  B, Dq, Hq, Wq, D, H, W, _stream(), batch=B)
     return glow
 
 
@@ -371,7 +374,7 @@ def warp(img: Tensor, disp: Tensor) -> Tensor:
     out = torch.empty_like(im)
     lx, ly = linspace_table(W, im.device), linspace_table(H, im.device)
     with torch.cuda.device(im.device):
-        _lib.call("az_warp_fwd", _ptr(im), _ptr(d), _ptr(lx), _ptr(ly), _ptr(out), B, C, H, W, _stream())
+        _lib.call("az_warp_fwd", _ptr(im), _ptr(d), _ptr(lx), _ptr(ly), _ptr(out), B, C, H, W, _stream(), batch=B)
     return out
 
 
@@ -391,7 +394,7 @@ def warp_backward(img: Tensor, disp: Tensor, gout: Tensor) -> Tuple[Tensor, Tens
     lx, ly = linspace_table(W, im.device), linspace_table(H, im.device)
     with torch.cuda.device(im.device):
         _lib.call("az_warp_bwd", _ptr(im), _ptr(d), _ptr(lx), _ptr(ly), _ptr(g), _ptr(gimg), _ptr(gdisp), B, C, H, W,
-                  _stream())
+                  _stream(), batch=B)
     return gimg, gdisp
 
 
@@ -427,7 +430,7 @@ def scatter_warp_op(img: Tensor, disp: Tensor) -> Tuple[Tensor, Tensor]:
     out = torch.empty_like(im)
     flags = torch.zeros((1,), dtype=torch.int32, device=im.device)  # bit 0: a positive, bit 1: a negative disparity
     with torch.cuda.device(im.device):
-        _lib.call("az_scatter_warp", _ptr(im), _ptr(d), _ptr(out), _ptr(flags), N, C, H, W, _stream())
+        _lib.call("az_scatter_warp", _ptr(im), _ptr(d), _ptr(out), _ptr(flags), N, C, H, W, _stream(), batch=N)
     return out, flags
 
 
@@ -454,7 +457,7 @@ def temporal_ir_pattern(frames: Tensor, ks: int, threshold: float) -> Tensor:
     pat = torch.empty((B, H, W), dtype=torch.float32, device=f.device)
     ws = torch.empty((_lib.query("az_temporal_ir_workspace_bytes", B, H, W),), dtype=torch.uint8, device=f.device)
     with torch.cuda.device(f.device):
-        _lib.call("az_temporal_ir", _ptr(f), _ptr(pat), _ptr(ws), B, T, H, W, ks, threshold, _stream())
+        _lib.call("az_temporal_ir", _ptr(f), _ptr(pat), _ptr(ws), B, T, H, W, ks, threshold, _stream(), batch=B)
     return pat
 
 
@@ -475,7 +478,7 @@ def local_contrast_norm(image: Tensor, kernel_size: int, eps: float) -> Tuple[Te
     normed = torch.empty((B, 1, H, W), dtype=torch.float32, device=im.device)
     std = torch.empty_like(normed)
     with torch.cuda.device(im.device):
-        _lib.call("az_local_contrast_norm", _ptr(im), _ptr(normed), _ptr(std), B, Cin, H, W, kernel_size, eps, _stream())
+        _lib.call("az_local_contrast_norm", _ptr(im), _ptr(normed), _ptr(std), B, Cin, H, W, kernel_size, eps, _stream(), batch=B)
     return normed, std
 
 

@@ -99,7 +99,7 @@ class ConcatVolumeFn(torch.autograd.Function):
                           memory_format=torch.channels_last_3d if ndhwc else torch.contiguous_format)
         with torch.cuda.device(L.device):
             _lib.call("az_concat_volume_fwd_ndhwc" if ndhwc else "az_concat_volume_fwd", _ptr(L), _ptr(R), _ptr(vol),
-                      B, C, H, W, int(num_disp), _stream())
+                      B, C, H, W, int(num_disp), _stream(), batch=B)
         ctx.dims = (B, C, H, W, int(num_disp))
         if channels_last and not ndhwc:  # C not a multiple of 4: torch's layout conversion (still on the device)
             vol = vol.contiguous(memory_format=torch.channels_last_3d)
@@ -121,7 +121,7 @@ class ConcatVolumeFn(torch.autograd.Function):
         gR = torch.empty((B, C, H, W), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(g.device):
             _lib.call("az_concat_volume_bwd_ndhwc" if ndhwc else "az_concat_volume_bwd", _ptr(g), _ptr(gL), _ptr(gR),
-                      B, C, H, W, Dq, _stream())
+                      B, C, H, W, Dq, _stream(), batch=B)
         return gL, gR, None, None
 
 
@@ -166,7 +166,7 @@ def volume_conv0(ref_feat, tgt_feat, wpacked, num_disp: int, scale=None, shift=N
     out = torch.empty((B, 32, int(num_disp), H, W), dtype=torch.float32, device=L.device)
     with torch.cuda.device(L.device):
         _lib.call("az_volume_conv0_fwd", _ptr(L), _ptr(R), _ptr(wp), _ptr(sc), _ptr(sh), _ptr(out), B, C, H, W, int(num_disp),
-                  1 if relu else 0, _stream())
+                  1 if relu else 0, _stream(), batch=B)
     return out
 
 
@@ -184,7 +184,7 @@ class GwcVolumeFn(torch.autograd.Function):
         vol = torch.empty((B, int(num_groups), int(num_disp), H, W), dtype=torch.float32, device=L.device)
         with torch.cuda.device(L.device):
             _lib.call("az_gwc_volume_fwd", _ptr(L), _ptr(R), _ptr(vol), B, C, H, W, int(num_disp), int(num_groups),
-                      _stream())
+                      _stream(), batch=B)
         ctx.save_for_backward(L, R)
         ctx.dims = (B, C, H, W, int(num_disp), int(num_groups))
         return vol
@@ -199,7 +199,7 @@ class GwcVolumeFn(torch.autograd.Function):
         gL = torch.empty_like(L) if ctx.needs_input_grad[0] else None
         gR = torch.empty_like(R) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(g.device):
-            _lib.call("az_gwc_volume_bwd", _ptr(g), _ptr(L), _ptr(R), _ptr(gL), _ptr(gR), B, C, H, W, Dq, G, _stream())
+            _lib.call("az_gwc_volume_bwd", _ptr(g), _ptr(L), _ptr(R), _ptr(gL), _ptr(gR), B, C, H, W, Dq, G, _stream(), batch=B)
         return gL, gR, None, None
 
 
@@ -225,7 +225,7 @@ class SoftArgminFn(torch.autograd.Function):
         need_bwd = ctx.needs_input_grad[0]
         lse = torch.empty((B, 2, H, W), dtype=torch.float32, device=c.device) if need_bwd else None
         with torch.cuda.device(c.device):
-            _lib.call("az_soft_argmin_fwd", _ptr(c), _ptr(disp), _ptr(lse), B, D, H, W, _stream())
+            _lib.call("az_soft_argmin_fwd", _ptr(c), _ptr(disp), _ptr(lse), B, D, H, W, _stream(), batch=B)
         if need_bwd:
             ctx.save_for_backward(c, disp, lse)
         return disp
@@ -239,7 +239,7 @@ class SoftArgminFn(torch.autograd.Function):
         g = _cuda_f32(gdisp, "grad_disp")
         gcost = torch.empty_like(c)
         with torch.cuda.device(c.device):
-            _lib.call("az_soft_argmin_bwd", _ptr(c), _ptr(disp), _ptr(lse), _ptr(g), _ptr(gcost), B, D, H, W, _stream())
+            _lib.call("az_soft_argmin_bwd", _ptr(c), _ptr(disp), _ptr(lse), _ptr(g), _ptr(gcost), B, D, H, W, _stream(), batch=B)
         return gcost
 
 
@@ -268,7 +268,7 @@ class UpsampleSoftArgminFn(torch.autograd.Function):
         need_bwd = ctx.needs_input_grad[0]
         stats = torch.empty((B, 2, H, W), dtype=torch.float32, device=c.device) if need_bwd else None
         with torch.cuda.device(c.device):
-            _lib.call("az_upsample_soft_argmin_fwd", _ptr(c), _ptr(disp), _ptr(stats), B, Dq, Hq, Wq, D, H, W, _stream())
+            _lib.call("az_upsample_soft_argmin_fwd", _ptr(c), _ptr(disp), _ptr(stats), B, Dq, Hq, Wq, D, H, W, _stream(), batch=B)
         if need_bwd:
             ctx.save_for_backward(c, disp, stats)
         ctx.dims = (B, Dq, Hq, Wq, D, H, W)
@@ -286,7 +286,7 @@ class UpsampleSoftArgminFn(torch.autograd.Function):
                          device=c.device)
         with torch.cuda.device(c.device):
             _lib.call("az_upsample_soft_argmin_bwd", _ptr(c), _ptr(disp), _ptr(stats), _ptr(g), _ptr(glow), _ptr(ws),
-                      B, Dq, Hq, Wq, D, H, W, _stream())
+                      B, Dq, Hq, Wq, D, H, W, _stream(), batch=B)
         return glow, None
 
 
@@ -313,7 +313,7 @@ class WarpFn(torch.autograd.Function):
         out = torch.empty_like(im)
         lx, ly = linspace_table(W, im.device), linspace_table(H, im.device)
         with torch.cuda.device(im.device):
-            _lib.call("az_warp_fwd", _ptr(im), _ptr(d), _ptr(lx), _ptr(ly), _ptr(out), B, C, H, W, _stream())
+            _lib.call("az_warp_fwd", _ptr(im), _ptr(d), _ptr(lx), _ptr(ly), _ptr(out), B, C, H, W, _stream(), batch=B)
         ctx.save_for_backward(im, d)
         return out
 
@@ -329,7 +329,7 @@ class WarpFn(torch.autograd.Function):
         lx, ly = linspace_table(W, im.device), linspace_table(H, im.device)
         with torch.cuda.device(im.device):
             _lib.call("az_warp_bwd", _ptr(im), _ptr(d), _ptr(lx), _ptr(ly), _ptr(g), _ptr(gimg), _ptr(gdisp),
-                      B, C, H, W, _stream())
+                      B, C, H, W, _stream(), batch=B)
         return gimg, gdisp
 
 
@@ -377,7 +377,10 @@ class ReprojLossFn(torch.autograd.Function):
         lx, ly = linspace_table(W, dev), linspace_table(H, dev)
         with torch.cuda.device(dev):
             _lib.call("az_reproj_loss_fwd", _ptr(t), _ptr(s), _ptr(d), float(sign), _ptr(mask_u8), _ptr(lx), _ptr(ly),
-                      int(ps), _ptr(warped), _ptr(gpre), _ptr(loss), _ptr(stats), _ptr(ws), B, C, H, W, _stream())
+                      int(ps), _ptr(warped), _ptr(gpre), _ptr(loss), _ptr(stats), _ptr(ws), B, C, H, W, _stream(), batch=B)
+        if B == 0:  # F.mse_loss of nothing (reprojection.py:118 on an empty batch) is NaN
+            loss.fill_(float("nan"))
+            stats.zero_()
         if need_bwd:
             ctx.save_for_backward(gpre, stats)
         ctx.meta = (B, C, H, W, int(ps), float(sign))
@@ -395,7 +398,7 @@ class ReprojLossFn(torch.autograd.Function):
         gdisp = torch.empty_like(gpre)
         with torch.cuda.device(gpre.device):
             _lib.call("az_reproj_loss_bwd", _ptr(gpre), _ptr(stats), _ptr(gl), sign, _ptr(gdisp), B, C, H, W, ps,
-                      _stream())
+                      _stream(), batch=B)
         return None, None, gdisp, None, None, None, None
 
 
@@ -420,7 +423,7 @@ def patch_fold(src, disp, ps: int, sign: float = -1.0):
     lx, ly = linspace_table(W, s.device), linspace_table(H, s.device)
     with torch.cuda.device(s.device):
         _lib.call("az_patch_fold", _ptr(s), _ptr(d), float(sign), _ptr(lx), _ptr(ly), int(ps), _ptr(vis), B, C, H, W,
-                  _stream())
+                  _stream(), batch=B)
     return vis
 
 
@@ -447,7 +450,7 @@ class _RescaleDispFn(torch.autograd.Function):
         m_o = torch.empty((B, 1, Ho, Wo), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.call("az_bilinear_rescale_fwd", _ptr(t), _ptr(s), _ptr(d), _ptr(mask_u8), _ptr(t_o), _ptr(s_o), _ptr(d_o),
-                      _ptr(m_o), B, C, H, W, Ho, Wo, inv, inv, float(r), _stream())
+                      _ptr(m_o), B, C, H, W, Ho, Wo, inv, inv, float(r), _stream(), batch=B)
         ctx.meta = (B, H, W, Ho, Wo, inv, float(r))
         ctx.mark_non_differentiable(t_o, s_o, m_o)
         return d_o, t_o, s_o, m_o
@@ -460,7 +463,7 @@ class _RescaleDispFn(torch.autograd.Function):
         g = _cuda_f32(gd, "grad_disp_rs")
         gin = torch.empty((B, 1, H, W), dtype=torch.float32, device=g.device)
         with torch.cuda.device(g.device):
-            _lib.call("az_bilinear_rescale_bwd", _ptr(g), _ptr(gin), B, H, W, Ho, Wo, inv, inv, r, _stream())
+            _lib.call("az_bilinear_rescale_bwd", _ptr(g), _ptr(gin), B, H, W, Ho, Wo, inv, inv, r, _stream(), batch=B)
         return gin, None, None, None, None
 
 
@@ -493,7 +496,7 @@ def scatter_warp(img, disp, check_sign: bool = True):
     out = torch.empty_like(img)
     flags = torch.zeros((1,), dtype=torch.int32, device=img.device) if check_sign else None
     with torch.cuda.device(img.device):
-        _lib.call("az_scatter_warp", _ptr(img), _ptr(disp), _ptr(out), _ptr(flags), N, C, H, W, _stream())
+        _lib.call("az_scatter_warp", _ptr(img), _ptr(disp), _ptr(out), _ptr(flags), N, C, H, W, _stream(), batch=N)
     if check_sign:
         assert int(flags.item()) != 3, "disparities must be all >= 0 or all <= 0"
     return out
@@ -515,7 +518,7 @@ def scatter_warp_gt(disp_r_2x, max_disp: float, check_sign: bool = True):
     mask = torch.empty((N, 1, H, W), dtype=torch.uint8, device=d.device)
     flags = torch.zeros((1,), dtype=torch.int32, device=d.device) if check_sign else None
     with torch.cuda.device(d.device):
-        _lib.call("az_scatter_warp_gt", _ptr(d), _ptr(out), _ptr(mask), _ptr(flags), float(max_disp), N, H2, W2, _stream())
+        _lib.call("az_scatter_warp_gt", _ptr(d), _ptr(out), _ptr(mask), _ptr(flags), float(max_disp), N, H2, W2, _stream(), batch=N)
     if check_sign:
         assert int(flags.item()) != 3, "disparities must be all >= 0 or all <= 0"
     return out, mask.view(torch.bool)
@@ -534,7 +537,7 @@ def temporal_ir_pattern(frames, ks: int = 11, threshold: float = 0.005):
     pat = torch.empty((B, H, W), dtype=torch.float32, device=f.device)
     ws = torch.empty((_lib.query("az_temporal_ir_workspace_bytes", B, H, W),), dtype=torch.uint8, device=f.device)
     with torch.cuda.device(f.device):
-        _lib.call("az_temporal_ir", _ptr(f), _ptr(pat), _ptr(ws), B, T, H, W, int(ks), float(threshold), _stream())
+        _lib.call("az_temporal_ir", _ptr(f), _ptr(pat), _ptr(ws), B, T, H, W, int(ks), float(threshold), _stream(), batch=B)
     return pat[0] if squeeze else pat
 
 
@@ -552,7 +555,7 @@ def local_contrast_norm(image, kernel_size: int = 9, eps: float = 1e-5):
     std = torch.empty_like(normed)
     with torch.cuda.device(im.device):
         _lib.call("az_local_contrast_norm", _ptr(im), _ptr(normed), _ptr(std), B, Cin, H, W, int(kernel_size),
-                  float(eps), _stream())
+                  float(eps), _stream(), batch=B)
     return normed, std
 
 
@@ -581,7 +584,9 @@ def error_metric_sums(disp_gt, depth_gt, disp_pred, mask, depth_pred=None, focal
     ws = torch.empty((_lib.query("az_error_metrics_workspace_bytes", B, H, W),), dtype=torch.uint8, device=dg.device)
     with torch.cuda.device(dg.device):
         _lib.call("az_error_metrics", _ptr(dg), _ptr(zg), _ptr(dp), _ptr(zp), _ptr(f), _ptr(bl), _ptr(m), _ptr(out),
-                  _ptr(ws), B, H, W, _stream())
+                  _ptr(ws), B, H, W, _stream(), batch=B)
+    if B == 0:
+        out.zero_()  # no pixel selected: compute_err_metric then reports NaN like torch.mean of nothing
     return out
 
 
@@ -603,5 +608,5 @@ def sim_ir_pattern(img_ir, img_no_ir, ks: int = 11, threshold: float = 0.005):
                      device=a.device)
     with torch.cuda.device(a.device):
         _lib.call("az_sim_ir_pattern", _ptr(a), _ptr(b), 1 if a.dtype == torch.uint8 else 0, _ptr(pat), _ptr(ws),
-                  B, H, W, int(ks), float(threshold), _stream())
+                  B, H, W, int(ks), float(threshold), _stream(), batch=B)
     return pat[0] if squeeze else pat

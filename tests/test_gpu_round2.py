@@ -327,7 +327,7 @@ def test_patch_loss_fold_v3_vs_round1_kernel_large(H, W, field):
             loss.backward()
             loss2, vis2 = ops.reproj_loss(Lg, Rg, dg.detach(), mg, ps=11, want_warped=True)
             torch.cuda.synchronize()
-        assert torch.equal(vis, vis2) and float(loss) == float(loss2)  # run-to-run and grad / no-grad instances agree
+        assert torch.equal(vis, vis2) and float(loss.detach()) == float(loss2.detach())  # run-to-run and grad / no-grad instances agree
         res[impl] = (loss.item(), vis, dg.grad)
     assert abs(res[1][0] - res[0][0]) <= 1e-6 * abs(res[0][0])
     close(res[1][1], res[0][1])
@@ -519,3 +519,57 @@ def test_gt_chain_matches_reference_chain(shape, sign):
     # and against the unfused calls of this library
     r_dev = F.interpolate(d2.to(DEV), scale_factor=0.5, mode="nearest", recompute_scale_factor=False)
     assert torch.equal(out, ops.scatter_warp(r_dev, r_dev.type(torch.int)))
+
+
+# --------------------------------------------------------------------------- empty batch (B = 0)
+def test_empty_batch_follows_the_reference():
+    """The reference's torch code accepts an empty batch (empty tensors out, NaN for the MSE of nothing -- checked on
+    the oracle below); the operators return the same shapes without enqueueing anything, forward and backward, through
+    both the autograd Functions and the torch.library ops."""
+    from activezero_b200 import _lib
+
+    L0 = torch.zeros(0, 4, 5, 12)
+    cost0 = torch.zeros(0, 8, 20, 48)
+    img0, disp0 = torch.zeros(0, 1, 20, 48), torch.zeros(0, 1, 20, 48)
+    mask0 = torch.zeros(0, 1, 20, 48, dtype=torch.bool)
+    Lg, Rg = L0.to(DEV).requires_grad_(True), L0.to(DEV).requires_grad_(True)
+    cg = cost0.to(DEV).requires_grad_(True)
+    before = _lib.launch_count
+
+    vol = ops.build_concat_volume(Lg, Rg, 3)
+    assert vol.shape == so.concat_volume(L0, L0, 3).shape == (0, 8, 3, 5, 12)
+    gvol = ops.build_gwc_volume(Lg, Rg, 3, 2)
+    assert gvol.shape == so.gwc_volume(L0, L0, 3, 2).shape
+    disp = ops.soft_argmin(cg)
+    assert disp.shape == so.soft_argmin(cost0).shape == (0, 1, 20, 48)
+    low = torch.zeros(0, 1, 2, 5, 12, device=DEV, requires_grad=True)
+    assert ops.upsample_soft_argmin(low, (8, 20, 48)).shape == (0, 1, 20, 48)
+    assert ops.warp(img0.to(DEV), disp).shape == so.apply_disparity(img0, disp0).shape
+
+    loss, vis, m = az_rp.get_reproj_error_patch(img0.to(DEV), img0.to(DEV), disp, mask0.to(DEV), ps=5)
+    rloss, rvis, rm = so.reproj_error_patch(img0, img0, disp0, mask0, ps=5)
+    assert torch.isnan(loss) and torch.isnan(rloss)
+    assert vis.shape == rvis.shape and m.shape == rm.shape and m.dtype == rm.dtype
+    loss1, warped1, _ = az_rp.get_reprojection_error_old(img0.to(DEV), img0.to(DEV), disp, mask0.to(DEV))
+    assert torch.isnan(loss1) and warped1.shape == img0.shape
+
+    (vol.sum() + gvol.sum() + disp.sum() + loss).backward()
+    assert Lg.grad.shape == L0.shape and Rg.grad.shape == L0.shape and cg.grad.shape == cost0.shape
+
+    out = ops.scatter_warp(img0.to(DEV), torch.zeros(0, 1, 20, 48, dtype=torch.int32, device=DEV))
+    assert out.shape == img0.shape
+    assert ops.temporal_ir_pattern(torch.zeros(0, 7, 20, 48, dtype=torch.uint8, device=DEV)).shape == (0, 20, 48)
+    normed, std = ops.local_contrast_norm(img0.to(DEV))
+    assert normed.shape == std.shape == img0.shape
+    sums = ops.error_metric_sums(disp0.to(DEV), disp0.to(DEV), disp0.to(DEV), mask0.to(DEV),
+                                 depth_pred=disp0.to(DEV))
+    assert torch.equal(sums.cpu(), torch.zeros(8, dtype=torch.float64))
+
+    ns = torch.ops.az_stereo
+    assert ns.concat_volume(Lg.detach(), Rg.detach(), 3, False).shape == (0, 8, 3, 5, 12)
+    d2, _ = ns.soft_argmin(cg.detach())
+    assert d2.shape == (0, 1, 20, 48)
+    l2 = ns.reproj_loss(img0.to(DEV), img0.to(DEV), d2, mask0.to(DEV), 5, -1.0)[0]
+    assert torch.isnan(l2)
+    torch.cuda.synchronize()
+    assert _lib.launch_count == before, "an empty batch must not enqueue a kernel"
