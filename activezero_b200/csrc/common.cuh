@@ -35,6 +35,22 @@ __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 
+// ---- 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256; 32-byte aligned addresses) ----------------
+struct __align__(32) float8 { float v[8]; };
+inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+__device__ __forceinline__ float8 ldg8(const float* p) {  // read-only path, like __ldg
+    float8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream8(float* p, const float8& r) {  // evict-first, like __stcs
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]),
+                 "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+                 : "memory");
+}
+
 // ---- block reductions ---------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -99,6 +99,70 @@ __global__ void __launch_bounds__(kFwdThreads) concat_fwd_vec4_kernel(const floa
 
 
 // ------------------------------------------------------------------------------------------
+// forward with 256-bit accesses (W % 8 == 0, 32-byte aligned bases): sm_100's LDG.E.256 / STG.E.256 halve the number
+// of store instructions and L1 requests of the store stream.  A thread owns 8 consecutive floats of one (b, channel)
+// plane and writes them to the kFwdDG = 8 consecutive disparity planes i0 .. i0+7, i0 a multiple of 8, so the right
+// half's shift by i = i0 + r is the window [8-r, 16-r) of two ALIGNED octets, A at x-i0-8 and B at x-i0 (an octet is
+// wholly inside or wholly left of its row): two loads and eight stores per thread, static register indices.
+// grid = (ceil(H*W/8 / THREADS), 2C * ceil(Dq/8), B); a CTA writes runs of THREADS*32 bytes.
+// ------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) concat_fwd_vec8_kernel(const float* __restrict__ L,
+                                                                  const float* __restrict__ R,
+                                                                  float* __restrict__ vol, int C, int H, int W,
+                                                                  int Dq, int ngroups) {
+    static_assert(kFwdDG == 8, "the octet window needs plane groups of 8");
+    const int W8 = W >> 3;
+    const int oc = blockIdx.y / ngroups, dg = blockIdx.y - oc * ngroups, b = blockIdx.z;
+    const int i0 = dg * kFwdDG, i1 = min(Dq, i0 + kFwdDG);
+    const bool right = oc >= C;
+    const int c = right ? oc - C : oc;
+    const int p = blockIdx.x * THREADS + threadIdx.x;
+    if (p >= H * W8) return;
+    const size_t HW = (size_t)H * W;
+    const int x = (p % W8) * 8;
+    const float* sp = (right ? R : L) + ((size_t)b * C + c) * HW + (size_t)p * 8;  // feature[y][x]
+    float* op = vol + ((size_t)b * 2 * C + oc) * Dq * HW + (size_t)p * 8;
+    if (!right) {
+        const float8 v = ldg8(sp);
+#pragma unroll
+        for (int r = 0; r < kFwdDG; ++r) {
+            const int i = i0 + r;
+            if (i >= i1) break;
+            float8 o = v;
+            if (x < i) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (x + k < i) o.v[k] = 0.f;
+            }
+            st_stream8(op + (size_t)i * HW, o);
+        }
+    } else {
+        float ab[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) ab[k] = 0.f;
+        if (x - i0 >= 0) {
+            const float8 Bv = ldg8(sp - i0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ab[8 + k] = Bv.v[k];
+        }
+        if (x - i0 - 8 >= 0) {
+            const float8 Av = ldg8(sp - i0 - 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ab[k] = Av.v[k];
+        }
+#pragma unroll
+        for (int r = 0; r < kFwdDG; ++r) {
+            if (i0 + r >= i1) break;
+            float8 o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] = ab[8 - r + k];
+            st_stream8(op + (size_t)(i0 + r) * HW, o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // forward through the bulk-store engine (round 2, north-star "TMA bulk copies"): the output never
 // crosses the register file.  The LSU only stages the input rows in shared memory (1/48 + 4/48 of the
 // output bytes); every output byte is written by cp.async.bulk shared -> global (SASS UBLKCP).
@@ -458,7 +522,7 @@ extern "C" int az_concat_volume_fwd(const float* L, const float* R, float* vol, 
         const int PAD = (int)((Dq + 3) / 4 * 4);
         const size_t smemL = (size_t)kBulkRowsL * W * 4, smemR = (size_t)4 * kBulkRowsR * (PAD + W) * 4;
         const size_t smemB = smemL > smemR ? smemL : smemR;
-        if (impl != 0 && smemB <= 200 * 1024 && C <= 65535 && Dq <= W) {
+        if ((impl == 1 || impl == 2) && smemB <= 200 * 1024 && C <= 65535 && Dq <= W) {
             const int nL = (int)ceil_div(H, kBulkRowsL), nR = (int)ceil_div(H, kBulkRowsR);
             cudaError_t e = cudaFuncSetAttribute(concat_fwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) return (int)e;
@@ -471,6 +535,17 @@ extern "C" int az_concat_volume_fwd(const float* L, const float* R, float* vol, 
                 concat_fwd_vec4_kernel<<<grid, kFwdThreads, 0, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq, (int)ngroups);
                 AZ_LAUNCH_CHECK();
             }
+            return 0;
+        }
+        // 3 / 4 / 5 = 256-bit loads and stores, CTAs of 128 / 256 / 64 threads (4 / 8 / 2 KB runs)
+        if (impl >= 3 && impl <= 5 && W % 8 == 0 && aligned32(L) && aligned32(R) && aligned32(vol) && 2 * C * ngroups <= 65535) {
+            const int64_t n8 = H * (W / 8);
+            const int nt = impl == 3 ? 128 : impl == 4 ? 256 : 64;
+            dim3 grid((unsigned)ceil_div(n8, nt), (unsigned)(2 * C * ngroups), (unsigned)B);
+            if (nt == 128) concat_fwd_vec8_kernel<128><<<grid, 128, 0, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq, (int)ngroups);
+            else if (nt == 256) concat_fwd_vec8_kernel<256><<<grid, 256, 0, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq, (int)ngroups);
+            else concat_fwd_vec8_kernel<64><<<grid, 64, 0, st>>>(L, R, vol, (int)C, (int)H, (int)W, (int)Dq, (int)ngroups);
+            AZ_LAUNCH_CHECK();
             return 0;
         }
         if (2 * C * ngroups <= 65535) {

@@ -94,7 +94,7 @@ def main():
             L, R = torch.randn(B, C, Hq, Wq, device=DEV), torch.randn(B, C, Hq, Wq, device=DEV)
             nb = 4 * (2 * C * Hq * Wq + 2 * C * Dq * Hq * Wq) * B
             ref = None
-            for v in (0, 1, 2):
+            for v in (0, 1, 2, 3, 4, 5, 0, 3):  # 3 / 4 / 5 = 256-bit loads + stores (128 / 256 / 64 threads); 0 and 3 repeated
                 with env(AZ_CONCAT_FWD=v):
                     ms = time_ms(lambda: ops.build_concat_volume(L, R, Dq))
                     out = ops.build_concat_volume(L, R, Dq)

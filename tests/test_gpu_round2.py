@@ -151,11 +151,12 @@ def test_gwc_kernel_variants(knobs, shape, dq, G):
 
 
 # --------------------------------------------------------------------------- kernel variants behind the tuning knobs
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("shape,dq", [((2, 32, 136, 240), 48), ((1, 4, 33, 64), 12), ((1, 3, 5, 8), 8), ((1, 32, 64, 128), 47),
-                                      ((1, 2, 40, 480), 72)])
+                                      ((1, 2, 40, 480), 72), ((1, 2, 3, 24), 29), ((1, 2, 3, 12), 5)])
 def test_concat_fwd_variants_bit_exact(impl, shape, dq):
-    """Register/LSU path, bulk-store path (cp.async.bulk shared->global) and the hybrid: all bit-exact."""
+    """Register/LSU path, bulk-store path (cp.async.bulk shared->global), the hybrid, and the 256-bit load/store forms
+    (3 / 4 / 5: CTAs of 128 / 256 / 64 threads; W % 8 != 0 falls through to the 128-bit kernel): all bit-exact."""
     torch.manual_seed(13)
     L, R = torch.randn(shape), torch.randn(shape)
     ref = so.concat_volume(L, R, dq)
