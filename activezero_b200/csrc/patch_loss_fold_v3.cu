@@ -571,7 +571,11 @@ static int launch(Args a, int B, int* nbands_out, cudaStream_t st) {
     if (per_sm > 65536 / (128 * threads)) per_sm = 65536 / (128 * threads);
     if (per_sm > 2048 / threads) per_sm = 2048 / threads;
     if (per_sm < 1) per_sm = 1;
-    const int64_t slots = (int64_t)kNumSMs * per_sm;
+    // AZ_PATCH_SMS (developer knob): size the bands for a partition of the GPU (a green context with fewer SMs,
+    // benchmarks/sm_partition_pipeline.py) instead of all 148 SMs
+    int sms = tuning("AZ_PATCH_SMS", kNumSMs);
+    if (sms < 1 || sms > kNumSMs) sms = kNumSMs;
+    const int64_t slots = (int64_t)sms * per_sm;
     int best_nb = 1;
     double best = 1e30;
     for (int nb = 1; nb <= H; ++nb) {

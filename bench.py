@@ -579,6 +579,55 @@ def run_b200(args, rank, world, local_rank):
                                   "frac": flop_nominal / (ms_v * 1e-3) / 1e12 / 1125.0}}
             del wconv, wp, Lv, Rv
 
+        # ---- informational: the same K steps software-pipelined across batches over two streams -- the patch loss of
+        # batch i (compute-bound, bands sized for 48 SMs: AZ_PATCH_SMS) runs UNDER the concat volume of batch i and the
+        # soft-argmin of batch i+1 (HBM-bound), which it cannot do inside one step (DESIGN.md section 4.10;
+        # benchmarks/sm_partition_pipeline.py also runs it on green-context SM partitions).  Every kernel of the K
+        # steps, the last loss included, lies inside the timed region.  Not part of value / e2e.
+        pipe = None
+        if world == 1 and not args.no_stock_variant:
+            try:
+                s_patch, s_hbm = torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Stream(device=dev)
+                keep = [None]
+
+                def _pipe(n):
+                    for _ in range(n):
+                        with torch.cuda.stream(s_hbm):
+                            d_ = ops.soft_argmin(cost)
+                            ready = torch.cuda.Event()
+                            ready.record(s_hbm)
+                            v_ = ops.build_concat_volume(L, R, DQ)
+                            del v_
+                        d_.record_stream(s_patch)  # allocated on s_hbm, read on s_patch: the allocator recycles the
+                        with torch.cuda.stream(s_patch):  # block only after s_patch has passed this point (no growth)
+                            s_patch.wait_event(ready)
+                            keep[0] = ops.reproj_loss(pat_L, pat_R, d_, mask, ps=PS, sign=-1.0, want_warped=True)
+
+                os.environ["AZ_PATCH_SMS"] = "48"
+                s_hbm.wait_stream(torch.cuda.current_stream())
+                s_patch.wait_stream(torch.cuda.current_stream())
+                _pipe(max(3, args.warmup))
+                torch.cuda.synchronize()
+                p0, ph, pp = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                p0.record(s_hbm)
+                _pipe(args.steps)
+                ph.record(s_hbm)
+                pp.record(s_patch)
+                torch.cuda.synchronize()
+                ms_pipe = max(p0.elapsed_time(ph), p0.elapsed_time(pp)) / args.steps
+                pipe = {"note": "informational: K steps pipelined across batches over two streams (eager launches): patch loss "
+                                "of batch i, bands sized for 48 SMs, under the concat volume of batch i and the soft-argmin of "
+                                "batch i+1; all work of the K steps inside the timed region",
+                        "ms_per_step": ms_pipe, "value": B / (ms_pipe * 1e-3), "unit": UNIT,
+                        "speedup_vs_eager_sequential": ms_eager / args.steps / ms_pipe,
+                        "loss": float(keep[0][0]),
+                        "pipeline_frac": sum(ALGO_BYTES.values()) / (ms_pipe * 1e-3) / 1e9 / _peaks()[0]}
+                keep[0] = None
+            except Exception as e:  # informational only: never take the bench line down
+                pipe = {"error": repr(e)}
+            finally:
+                os.environ.pop("AZ_PATCH_SMS", None)
+
     ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train, ms_h2d, ms_fused_k, ms_eager = dist_util.max_over_ranks(
         [ms_total, ms_e2e, ms_fused, ms_fused_e2e, ms_train, ms_h2d, ms_fused_k, ms_eager], dev)
 
@@ -674,6 +723,8 @@ def run_b200(args, rank, world, local_rank):
             line["variant_stock_torch_gpu"] = stock
         if vconv is not None:
             line["variant_implicit_volume_conv"] = vconv
+        if pipe is not None:
+            line["variant_batch_pipelined"] = pipe
         if world == 1 and not args.no_cpu_baseline:
             pairs_s, _, cores = time_cpu_reference(12, 1)  # ~10 s of CPU work on the box's host cores
             line["cpu_baseline"] = {"value": pairs_s, "unit": UNIT, "cores": cores, "kind": "port",

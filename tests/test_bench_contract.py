@@ -1,5 +1,5 @@
 """CPU: the one-JSON-line contract of bench.py.  The B200 arm cannot run here, so its committed output
-(profiles/r2_bench_final.json, written by `python bench.py` on a B200) is checked for the keys
+(profiles/r2_bench_head.json, written by `python bench.py` on a B200) is checked for the keys
 and the internal consistency the driver relies on; the reference arm (CPU oracle) is executed for real."""
 import json
 import os
@@ -12,7 +12,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_committed_b200_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_final.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_head.json")))
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
     assert d["metric"] in base["metric"] and d["unit"] == "pairs/s" and d["higher_is_better"] is True
@@ -45,6 +45,10 @@ def test_committed_b200_line_has_the_contract_keys():
     assert d["variant_fused_upsample"]["fused_soft_argmin_kernel"]["bound"] == "mufu"
     vc = d["variant_implicit_volume_conv"]
     assert vc["roofline"]["bound"] == "tensor" and 0 < vc["roofline"]["frac"] < 1 and vc["speedup"] > 1.0
+    # the batch-pipelined schedule (patch loss of batch i under the HBM kernels of batch i+1): informational, faster
+    bp = d["variant_batch_pipelined"]
+    assert "error" not in bp and bp["unit"] == "pairs/s" and bp["ms_per_step"] < d["ms_per_step_eager"]
+    assert abs(bp["value"] - pairs / (bp["ms_per_step"] * 1e-3)) <= 1e-6 * bp["value"] and 0.8 < bp["pipeline_frac"] < 1.0
 
 
 def test_reference_arm_runs_and_prints_one_json_line():
@@ -55,7 +59,7 @@ def test_reference_arm_runs_and_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and BASE_KEYS <= set(d)
-    ref = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_final.json")))
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_head.json")))
     assert d["metric"] == ref["metric"] and d["unit"] == ref["unit"] and d["higher_is_better"] is True
     assert d["config"] == ref["config"]  # the driver compares the two arms' config dicts (`same_config`)
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
